@@ -1,0 +1,563 @@
+// api.cu — host orchestration and the C ABI (include/psoap_b200.h) of the sm_100a PSOAP likelihood path.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/psoap_b200.h"
+#include "chol.cuh"
+#include "common.cuh"
+#include "fill.cuh"
+#include "orbit.cuh"
+
+using namespace psoap;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(PSOAP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+#define LAUNCH_CHECK()                                                                           \
+    do {                                                                                         \
+        ++g_launches;                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                     \
+        if (e_ != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
+
+std::once_flag g_attr_once;
+int g_attr_status = 0;
+int set_kernel_attributes() {
+    std::call_once(g_attr_once, [] {
+        cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        g_attr_status = (int)e;
+    });
+    if (g_attr_status != 0)
+        return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
+    return PSOAP_OK;
+}
+
+// Device scratch of one factorisation: W [Nt x Nt] (Nt = padded total dimension), two panel buffers,
+// L_kk^-1, residual, y, accumulators, info.
+struct FactorWs {
+    double* W;
+    double* P[2];
+    double* Linv;
+    double* rvec;
+    double* y;
+    double* acc;
+    int* info;
+    int64_t Nt;
+};
+
+size_t factor_ws_bytes(int64_t Nt) {
+    size_t b = 0;
+    b += align_up((size_t)Nt * Nt * 8, 256);
+    b += 2 * align_up((size_t)Nt * NB * 8, 256);
+    b += align_up((size_t)NB * NB * 8, 256);
+    b += 2 * align_up((size_t)Nt * 8, 256);
+    b += align_up(8 * 8, 256);
+    b += align_up(2 * 4, 256);
+    return b;
+}
+
+void carve_factor_ws(char* base, int64_t Nt, FactorWs* ws, bool with_W) {
+    char* p = base;
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+    ws->Nt = Nt;
+    ws->W = with_W ? (double*)take((size_t)Nt * Nt * 8) : nullptr;
+    ws->P[0] = (double*)take((size_t)Nt * NB * 8);
+    ws->P[1] = (double*)take((size_t)Nt * NB * 8);
+    ws->Linv = (double*)take((size_t)NB * NB * 8);
+    ws->rvec = (double*)take((size_t)Nt * 8);
+    ws->y = (double*)take((size_t)Nt * 8);
+    ws->acc = (double*)take(8 * 8);
+    ws->info = (int*)take(2 * 4);
+}
+
+// Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
+// (T_elim == T_total: plain Cholesky).  The trailing block is left holding the Schur complement.
+int launch_factor(cudaStream_t st, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
+                  const int* sentinel, double* result) {
+    for (int kb = 0; kb < T_elim; ++kb) {
+        const int is_last = (kb == T_elim - 1);
+        const int kbeg = (kb == 0) ? (pad / BK) * BK : 0;
+        double* P = ws.P[kb & 1];
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
+                                                      ws.info, sentinel, is_last, result);
+        LAUNCH_CHECK();
+        const int R = T_total - kb - 1;
+        if (R <= 0) continue;
+        trsm_kernel<<<2 * R, 256, GEMM_SMEM, st>>>(W, ld, kb, kbeg, ws.Linv, P, ws.Nt);
+        LAUNCH_CHECK();
+        const int ntiles = R * (R + 1);
+        syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, ld, kb, kbeg, P, ws.Nt, ntiles, ws.y + (int64_t)kb * NB,
+                                                        ws.rvec);
+        LAUNCH_CHECK();
+    }
+    return PSOAP_OK;
+}
+
+template <int NCOMP>
+void launch_fill_lower_t(cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
+                         const double* sigma, const double* fl, double mu, const GpParams& gp, const FactorWs& ws) {
+    dim3 grid(T, T);
+    fill_lower_kernel<NCOMP><<<grid, 256, 0, st>>>(W, ld, pad, zs, sigma, fl, mu, gp, ws.rvec, ws.acc, ws.info);
+}
+
+int launch_fill_lower(int ncomp, cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
+                      const double* sigma, const double* fl, double mu, const GpParams& gp, const FactorWs& ws) {
+    if (ncomp == 1) launch_fill_lower_t<1>(st, W, ld, T, pad, zs, sigma, fl, mu, gp, ws);
+    else if (ncomp == 2) launch_fill_lower_t<2>(st, W, ld, T, pad, zs, sigma, fl, mu, gp, ws);
+    else launch_fill_lower_t<3>(st, W, ld, T, pad, zs, sigma, fl, mu, gp, ws);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+// fill + factor + fused solve of one chunk on stream st
+int launch_chunk(cudaStream_t st, int ncomp, int64_t N, const ZSource& zs, const double* fl, const double* sigma,
+                 double mu, const GpParams& gp, const FactorWs& ws, const int* sentinel, double* result) {
+    const int64_t Np = padded_dim(N);
+    const int T = (int)(Np / NB);
+    const int pad = (int)(Np - N);
+    int rc = launch_fill_lower(ncomp, st, ws.W, Np, T, pad, zs, sigma, fl, mu, gp, ws);
+    if (rc) return rc;
+    return launch_factor(st, ws.W, Np, T, T, pad, ws, sentinel, result);
+}
+
+__global__ void write_result_kernel(double* result, double lnlike, double logdet, double quad, double info) {
+    result[0] = lnlike; result[1] = logdet; result[2] = quad; result[3] = info;
+}
+
+bool make_gp(int ncomp, const double* amp, const double* l, GpParams* gp) {
+    bool neg = false;
+    gp->dev = nullptr;
+    for (int c = 0; c < 3; ++c) { gp->amp[c] = 0; gp->l[c] = 1; }
+    for (int c = 0; c < ncomp; ++c) {
+        gp->amp[c] = amp[c];
+        gp->l[c] = l[c];
+        if (amp[c] < 0.0 || l[c] < 0.0) neg = true;
+    }
+    return neg;
+}
+
+ZSource direct_z(const double* f, const double* g, const double* h) {
+    ZSource zs;
+    zs.lwl[0] = f; zs.lwl[1] = g; zs.lwl[2] = h;
+    zs.epoch = nullptr; zs.vel = nullptr; zs.n_epochs = 0; zs.shift = 0;
+    return zs;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+const char* psoap_last_error(void) { return g_err.c_str(); }
+int psoap_version(void) { return 100; }
+int psoap_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t psoap_launch_count(void) { return g_launches.load(); }
+int psoap_model_ncomp(int model) { return (model >= 1 && model <= 5) ? model_ncomp(model) : 0; }
+int psoap_model_norb(int model) { return (model >= 1 && model <= 5) ? model_norb(model) : 0; }
+
+// ---- fills ------------------------------------------------------------------------------------------
+int psoap_fill_v11(int ncomp, double* mat, int64_t ld, int64_t N, const double* lwl_f, const double* lwl_g,
+                   const double* lwl_h, const double* amp, const double* l, void* stream) {
+    if (ncomp < 1 || ncomp > 3 || !mat || !lwl_f || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h) || ld < N || N < 0 ||
+        N > (1 << 30))
+        return fail(PSOAP_ERR_ARG, "psoap_fill_v11: bad arguments");
+    if (N == 0) return PSOAP_OK;
+    GpParams gp;
+    make_gp(ncomp, amp, l, &gp);
+    ZSource zs = direct_z(lwl_f, lwl_g, lwl_h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = (int)((N + 63) / 64);
+    dim3 grid(T, T);
+    if (ncomp == 1) fill_full_kernel<1><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
+    else if (ncomp == 2) fill_full_kernel<2><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
+    else fill_full_kernel<3><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+int psoap_fill_v12n(int ncomp, double* mat, int64_t ld, int64_t M, int64_t N, const double* const* rows,
+                    const double* const* cols, const double* amp, const double* l, void* stream) {
+    if (ncomp < 1 || ncomp > 3 || !mat || !rows || !cols || !amp || !l || ld < N || M < 0 || N < 0)
+        return fail(PSOAP_ERR_ARG, "psoap_fill_v12n: bad arguments");
+    if (M == 0 || N == 0) return PSOAP_OK;
+    GpParams gp;
+    make_gp(ncomp, amp, l, &gp);
+    V12Src src;
+    for (int c = 0; c < 3; ++c) {
+        src.rows[c] = c < ncomp ? rows[c] : nullptr;
+        src.cols[c] = c < ncomp ? cols[c] : nullptr;
+        if (c < ncomp && (!rows[c] || !cols[c])) return fail(PSOAP_ERR_ARG, "psoap_fill_v12n: null vector");
+    }
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ncomp == 1) fill_v12_kernel<1><<<grid, 256, 0, st>>>(mat, ld, (int)M, (int)N, src, gp);
+    else if (ncomp == 2) fill_v12_kernel<2><<<grid, 256, 0, st>>>(mat, ld, (int)M, (int)N, src, gp);
+    else fill_v12_kernel<3><<<grid, 256, 0, st>>>(mat, ld, (int)M, (int)N, src, gp);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+int psoap_fill_v12(double* mat, int64_t ld, int64_t M, int64_t N, const double* rows, const double* cols, double amp,
+                   double l, void* stream) {
+    return psoap_fill_v12n(1, mat, ld, M, N, &rows, &cols, &amp, &l, stream);
+}
+
+int psoap_replicate_wls(double* out, const double* lwl, const int32_t* epoch, int64_t N, const double* vel, int ncomp,
+                        int n_epochs, void* stream) {
+    if (!out || !lwl || !epoch || !vel || ncomp < 1 || ncomp > 3 || N < 0)
+        return fail(PSOAP_ERR_ARG, "psoap_replicate_wls: bad arguments");
+    if (N == 0) return PSOAP_OK;
+    ZSource zs = direct_z(lwl, nullptr, nullptr);
+    zs.epoch = epoch; zs.vel = vel; zs.n_epochs = n_epochs; zs.shift = 1;
+    replicate_wls_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, zs, N, ncomp);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+int psoap_orbit_velocities(int model, const double* p_orb, const double* dates, int n_epochs, double* vel, int* flag,
+                           void* stream) {
+    if (model < 1 || model > 5 || !p_orb || !dates || !vel || n_epochs < 0)
+        return fail(PSOAP_ERR_ARG, "psoap_orbit_velocities: bad arguments");
+    if (n_epochs == 0) return PSOAP_OK;
+    orbit_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(model, p_orb, dates, n_epochs, vel, flag, 0);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+// ---- likelihood -------------------------------------------------------------------------------------
+size_t psoap_lnlike_workspace_bytes(int64_t N) { return factor_ws_bytes(padded_dim(std::max<int64_t>(N, 1))); }
+
+int psoap_lnlike(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h, const double* fl,
+                 const double* sigma, const double* amp, const double* l, double mu_GP, void* workspace,
+                 size_t workspace_bytes, psoap_result* result, void* stream) {
+    if (ncomp < 1 || ncomp > 3 || N < 1 || N > 200000 || !lwl_f || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h) || !fl ||
+        !sigma || !amp || !l || !result)
+        return fail(PSOAP_ERR_ARG, "psoap_lnlike: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    GpParams gp;
+    if (make_gp(ncomp, amp, l, &gp)) {  // covariance.py:317-318: negative hyper-parameters -> -inf
+        write_result_kernel<<<1, 1, 0, st>>>((double*)result, -INFINITY, 0.0, 0.0, 0.0);
+        LAUNCH_CHECK();
+        return PSOAP_OK;
+    }
+    if (!workspace || workspace_bytes < psoap_lnlike_workspace_bytes(N) || ((uintptr_t)workspace & 255))
+        return fail(PSOAP_ERR_WORKSPACE, "psoap_lnlike: workspace too small or not 256-byte aligned");
+    int rc = set_kernel_attributes();
+    if (rc) return rc;
+    FactorWs ws;
+    carve_factor_ws((char*)workspace, padded_dim(N), &ws, true);
+    return launch_chunk(st, ncomp, N, direct_z(lwl_f, lwl_g, lwl_h), fl, sigma, mu_GP, gp, ws, nullptr, (double*)result);
+}
+
+namespace {
+struct HostCache {
+    std::mutex mu;
+    void* buf = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+} g_hc;
+}
+
+int psoap_lnlike_host(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h,
+                      const double* fl, const double* sigma, const double* amp, const double* l, double mu_GP,
+                      psoap_result* result) {
+    if (ncomp < 1 || ncomp > 3 || N < 1 || !lwl_f || !fl || !sigma || !result)
+        return fail(PSOAP_ERR_ARG, "psoap_lnlike_host: bad arguments");
+    std::lock_guard<std::mutex> lock(g_hc.mu);
+    const size_t vec = align_up((size_t)N * 8, 256);
+    const size_t need = psoap_lnlike_workspace_bytes(N) + 5 * vec + 256;
+    if (g_hc.bytes < need) {
+        if (g_hc.buf) cudaFree(g_hc.buf);
+        g_hc.buf = nullptr; g_hc.bytes = 0;
+        CUDA_TRY(cudaMalloc(&g_hc.buf, need));
+        g_hc.bytes = need;
+    }
+    if (!g_hc.st) CUDA_TRY(cudaStreamCreateWithFlags(&g_hc.st, cudaStreamNonBlocking));
+    char* base = (char*)g_hc.buf;
+    double* d[5];
+    const double* h[5] = {lwl_f, lwl_g, lwl_h, fl, sigma};
+    for (int i = 0; i < 5; ++i) {
+        d[i] = (double*)(base + i * vec);
+        if (h[i] && (i >= 3 || i < ncomp)) CUDA_TRY(cudaMemcpyAsync(d[i], h[i], (size_t)N * 8, cudaMemcpyHostToDevice, g_hc.st));
+    }
+    psoap_result* dres = (psoap_result*)(base + 5 * vec);
+    void* wsp = base + 5 * vec + 256;
+    int rc = psoap_lnlike(ncomp, N, d[0], ncomp > 1 ? d[1] : nullptr, ncomp > 2 ? d[2] : nullptr, d[3], d[4], amp, l, mu_GP,
+                          wsp, g_hc.bytes - 5 * vec - 256, dres, g_hc.st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(result, dres, sizeof(psoap_result), cudaMemcpyDeviceToHost, g_hc.st));
+    CUDA_TRY(cudaStreamSynchronize(g_hc.st));
+    return PSOAP_OK;
+}
+
+// ---- Schur complement of a bordered matrix (prediction) -----------------------------------------------
+size_t psoap_schur_workspace_bytes(int64_t n, int64_t m) {
+    const int64_t Nt = padded_dim(n) + padded_dim(std::max<int64_t>(m, 0));
+    return factor_ws_bytes(Nt) - align_up((size_t)Nt * Nt * 8, 256);
+}
+
+// S: column-major [Nt, ld] with Nt = padded(n) + padded(m).  The caller lays the leading block out with
+// FRONT padding (identity in the first padded(n) - n rows/cols) and the border from row padded(n) on;
+// rows beyond padded(n) + m are dead padding.  rvec (residual over all Nt rows) is taken from / returned in
+// the workspace through psoap_schur_residual.
+int psoap_schur(double* S, int64_t ld, int64_t n, int64_t m, void* workspace, size_t workspace_bytes,
+                psoap_result* result, void* stream) {
+    if (!S || n < 1 || m < 0 || !workspace || !result) return fail(PSOAP_ERR_ARG, "psoap_schur: bad arguments");
+    const int64_t Nn = padded_dim(n), Nt = Nn + padded_dim(m);
+    if (ld < Nt || (ld & 1) || ((uintptr_t)S & 15)) return fail(PSOAP_ERR_ARG, "psoap_schur: ld/alignment");
+    if (workspace_bytes < psoap_schur_workspace_bytes(n, m) || ((uintptr_t)workspace & 255))
+        return fail(PSOAP_ERR_WORKSPACE, "psoap_schur: workspace too small or misaligned");
+    int rc = set_kernel_attributes();
+    if (rc) return rc;
+    FactorWs ws;
+    carve_factor_ws((char*)workspace, Nt, &ws, false);
+    return launch_factor((cudaStream_t)stream, S, ld, (int)(Nn / NB), (int)(Nt / NB), (int)(Nn - n), ws, nullptr,
+                         (double*)result);
+}
+
+}  // extern "C"
+
+// The residual / accumulator part of a Schur workspace, for the host-side prediction code.
+extern "C" int psoap_schur_views(void* workspace, int64_t n, int64_t m, double** rvec, double** acc, int** info) {
+    const int64_t Nt = padded_dim(n) + padded_dim(std::max<int64_t>(m, 0));
+    FactorWs ws;
+    carve_factor_ws((char*)workspace, Nt, &ws, false);
+    if (rvec) *rvec = ws.rvec;
+    if (acc) *acc = ws.acc;
+    if (info) *info = ws.info;
+    return PSOAP_OK;
+}
+
+// ======================================================================================================
+// Chunk farm
+// ======================================================================================================
+struct psoap_farm {
+    int model = 0, ncomp = 0, norb = 0, nchunks = 0, nbranch = 0;
+    double mu = 1.0;
+    std::vector<psoap_chunk> chunks;
+    std::vector<FactorWs> branch_ws;
+    std::vector<std::vector<int>> branch_chunks;
+    double* p_buf = nullptr;          // [32] parameter vector the graph reads
+    double* results = nullptr;        // [nchunks][4]
+    double* vel = nullptr;            // per chunk [3 * n_epochs]
+    int* flags = nullptr;             // per chunk sentinel
+    OrbitDesc* descs = nullptr;       // device
+    std::vector<size_t> vel_off;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> events;
+    int launches = 0;
+};
+
+namespace {
+size_t farm_small_bytes(int nchunks, const int32_t* n_epochs, std::vector<size_t>* vel_off) {
+    size_t b = 0;
+    b += align_up(32 * 8, 256);                       // p_buf
+    b += align_up((size_t)nchunks * 4 * 8, 256);      // results
+    b += align_up((size_t)nchunks * 4, 256);          // flags
+    b += align_up((size_t)nchunks * sizeof(OrbitDesc), 256);
+    size_t v = 0;
+    for (int i = 0; i < nchunks; ++i) {
+        if (vel_off) vel_off->push_back(v);
+        v += align_up((size_t)3 * n_epochs[i] * 8, 256);
+    }
+    return b + v;
+}
+}  // namespace
+
+extern "C" {
+
+size_t psoap_farm_workspace_bytes(int nchunks, const int64_t* N, const int32_t* n_epochs, int nbranch) {
+    if (nchunks < 1 || !N || !n_epochs) return 0;
+    nbranch = std::max(1, std::min(nbranch, nchunks));
+    int64_t nmax = 0;
+    for (int i = 0; i < nchunks; ++i) nmax = std::max(nmax, N[i]);
+    return farm_small_bytes(nchunks, n_epochs, nullptr) + (size_t)nbranch * factor_ws_bytes(padded_dim(nmax));
+}
+
+int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chunk* chunks, int nbranch, double mu_GP,
+                      void* workspace, size_t workspace_bytes) {
+    if (!out || model < 1 || model > 5 || nchunks < 1 || !chunks || !workspace || ((uintptr_t)workspace & 255))
+        return fail(PSOAP_ERR_ARG, "psoap_farm_create: bad arguments");
+    nbranch = std::max(1, std::min(nbranch, nchunks));
+    std::vector<int64_t> Ns(nchunks);
+    std::vector<int32_t> nes(nchunks);
+    for (int i = 0; i < nchunks; ++i) {
+        if (chunks[i].N < 1 || chunks[i].n_epochs < 1 || !chunks[i].lwl || !chunks[i].epoch || !chunks[i].fl ||
+            !chunks[i].sigma || !chunks[i].dates)
+            return fail(PSOAP_ERR_ARG, "psoap_farm_create: bad chunk descriptor");
+        Ns[i] = chunks[i].N;
+        nes[i] = chunks[i].n_epochs;
+    }
+    if (workspace_bytes < psoap_farm_workspace_bytes(nchunks, Ns.data(), nes.data(), nbranch))
+        return fail(PSOAP_ERR_WORKSPACE, "psoap_farm_create: workspace too small");
+    int rc = set_kernel_attributes();
+    if (rc) return rc;
+
+    psoap_farm* f = new psoap_farm();
+    f->model = model; f->ncomp = model_ncomp(model); f->norb = model_norb(model);
+    f->nchunks = nchunks; f->nbranch = nbranch; f->mu = mu_GP;
+    f->chunks.assign(chunks, chunks + nchunks);
+    char* p = (char*)workspace;
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+    f->p_buf = (double*)take(32 * 8);
+    f->results = (double*)take((size_t)nchunks * 4 * 8);
+    f->flags = (int*)take((size_t)nchunks * 4);
+    f->descs = (OrbitDesc*)take((size_t)nchunks * sizeof(OrbitDesc));
+    farm_small_bytes(nchunks, nes.data(), &f->vel_off);
+    f->vel = (double*)p;
+    p += f->vel_off.back() + align_up((size_t)3 * nes.back() * 8, 256);
+    int64_t nmax = *std::max_element(Ns.begin(), Ns.end());
+    const size_t per_branch = factor_ws_bytes(padded_dim(nmax));
+    f->branch_ws.resize(nbranch);
+    for (int b = 0; b < nbranch; ++b) carve_factor_ws(p + (size_t)b * per_branch, padded_dim(nmax), &f->branch_ws[b], true);
+
+    // orbit descriptors
+    std::vector<OrbitDesc> hd(nchunks);
+    for (int i = 0; i < nchunks; ++i) {
+        hd[i].dates = chunks[i].dates;
+        hd[i].vel = (double*)((char*)f->vel + f->vel_off[i]);
+        hd[i].flag = f->flags + i;
+        hd[i].n_epochs = chunks[i].n_epochs;
+    }
+    cudaError_t e = cudaMemcpy(f->descs, hd.data(), (size_t)nchunks * sizeof(OrbitDesc), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete f; return fail(PSOAP_ERR_CUDA, std::string("farm descs: ") + cudaGetErrorString(e)); }
+
+    // LPT (longest processing time first) assignment of chunks to branches by N^3
+    std::vector<int> order(nchunks);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Ns[a] > Ns[b]; });
+    std::vector<double> load(nbranch, 0.0);
+    f->branch_chunks.assign(nbranch, {});
+    for (int idx : order) {
+        int b = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        f->branch_chunks[b].push_back(idx);
+        load[b] += (double)Ns[idx] * Ns[idx] * Ns[idx];
+    }
+
+    // capture the whole evaluation into one CUDA graph
+    f->streams.resize(nbranch + 1);
+    f->events.resize(nbranch + 1);
+    for (auto& s : f->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (auto& ev : f->events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaStream_t s0 = f->streams[nbranch];
+    const int64_t before = g_launches.load();
+    e = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { psoap_farm_destroy(f); return fail(PSOAP_ERR_CUDA, std::string("begin capture: ") + cudaGetErrorString(e)); }
+    orbit_farm_kernel<<<nchunks, 64, 0, s0>>>(model, f->p_buf, f->descs);
+    ++g_launches;
+    cudaEventRecord(f->events[nbranch], s0);
+    GpParams gp;
+    gp.dev = f->p_buf + f->norb;
+    for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
+    rc = PSOAP_OK;
+    for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
+        cudaStream_t sb = f->streams[b];
+        cudaStreamWaitEvent(sb, f->events[nbranch], 0);
+        for (int idx : f->branch_chunks[b]) {
+            const psoap_chunk& ch = f->chunks[idx];
+            ZSource zs;
+            zs.lwl[0] = ch.lwl; zs.lwl[1] = nullptr; zs.lwl[2] = nullptr;
+            zs.epoch = ch.epoch; zs.vel = hd[idx].vel; zs.n_epochs = ch.n_epochs; zs.shift = 1;
+            FactorWs ws = f->branch_ws[b];
+            ws.Nt = padded_dim(ch.N);
+            rc = launch_chunk(sb, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + idx, f->results + 4 * idx);
+            if (rc) break;
+        }
+        cudaEventRecord(f->events[b], sb);
+        cudaStreamWaitEvent(s0, f->events[b], 0);
+    }
+    e = cudaStreamEndCapture(s0, &f->graph);
+    f->launches = (int)(g_launches.load() - before);
+    g_launches = before;  // capture is not execution
+    if (rc != PSOAP_OK) { psoap_farm_destroy(f); return rc; }
+    if (e != cudaSuccess) { psoap_farm_destroy(f); return fail(PSOAP_ERR_CUDA, std::string("end capture: ") + cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(&f->exec, f->graph, 0);
+    if (e != cudaSuccess) { psoap_farm_destroy(f); return fail(PSOAP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+    *out = f;
+    return PSOAP_OK;
+}
+
+int psoap_farm_lnprob(psoap_farm* f, const double* p_dev, psoap_result* results_dev, void* stream) {
+    if (!f || !p_dev || !results_dev) return fail(PSOAP_ERR_ARG, "psoap_farm_lnprob: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = f->norb + 2 * f->ncomp;
+    CUDA_TRY(cudaMemcpyAsync(f->p_buf, p_dev, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGraphLaunch(f->exec, st));
+    g_launches += f->launches;
+    CUDA_TRY(cudaMemcpyAsync(results_dev, f->results, (size_t)f->nchunks * sizeof(psoap_result), cudaMemcpyDeviceToDevice, st));
+    return PSOAP_OK;
+}
+
+int psoap_farm_launches_per_eval(const psoap_farm* f) { return f ? f->launches : 0; }
+
+int psoap_farm_destroy(psoap_farm* f) {
+    if (!f) return PSOAP_OK;
+    if (f->exec) cudaGraphExecDestroy(f->exec);
+    if (f->graph) cudaGraphDestroy(f->graph);
+    for (auto& s : f->streams) if (s) cudaStreamDestroy(s);
+    for (auto& ev : f->events) if (ev) cudaEventDestroy(ev);
+    delete f;
+    return PSOAP_OK;
+}
+
+int psoap_fp64_peak_tflops(double* tflops_out) {
+    if (!tflops_out) return fail(PSOAP_ERR_ARG, "psoap_fp64_peak_tflops: null");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)sms * 512 * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 20000;
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<sms, 512>>>(out, iters);
+        cudaEventRecord(e1);
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops_out = 2.0 * 256 * 8 * (double)iters * 16 * sms / (best * 1e-3) * 1e-12;
+    return PSOAP_OK;
+}
+
+}  // extern "C"

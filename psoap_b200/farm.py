@@ -1,0 +1,164 @@
+"""ChunkFarm — the B200 replacement of the reference's multiprocessing chunk farm
+(psoap/sample_parallel.py: Worker.initialize :126-166, Worker.lnprob :168-198, master lnprob :371-390).
+
+The reference forks one process per chunk; each keeps its chunk resident and, per proposal, receives the
+parameter vector over a Pipe and sends one float back; the master np.sum()s them.  Here every rank (one process
+per GPU) owns a static subset of the chunks (longest-processing-time partition by N^3), keeps them resident in
+HBM, and evaluates all of them with ONE CUDA-graph launch: orbit velocities -> Doppler-shifted covariance fill
+-> blocked FP64 Cholesky with fused solve/logdet, several chunks in flight on independent graph branches.
+Per proposal only the parameter vector goes down and one record per chunk comes back.  Across ranks the
+per-chunk log-likelihoods are combined with a single all-reduce of a length-n_chunks FP64 vector (own entries
+filled, others zero: exact and order independent), then summed in chunk order like the reference's np.sum.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .data import epoch_index
+
+
+def lpt_partition(costs, nparts):
+    """Longest-processing-time-first partition: returns a list of index lists, deterministic."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * nparts
+    parts = [[] for _ in range(nparts)]
+    for i in order:
+        b = min(range(nparts), key=lambda k: (loads[k], k))
+        parts[b].append(i)
+        loads[b] += costs[i]
+    return parts
+
+
+def chunk_cost(N):
+    return float(N) ** 3
+
+
+class ChunkFarm:
+    """model: "SB1" | "SB2" | "ST1" | "ST2" | "ST3".
+    chunks: list of dicts with lwl, fl, sigma (masked 1-D), mask [n_epochs, n_pix] (or `epoch` int32 [N]) and
+    date1D — the attributes a reference Chunk exposes after apply_mask() (data.py:120-147).
+    rank/world_size: static partition of the chunks over GPUs; process_group: torch.distributed group (or None).
+    """
+
+    def __init__(self, model, chunks, mu_GP=1.0, soften=1.0, nbranch=8, rank=0, world_size=1, process_group=None):
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        self.model = model
+        self.n_chunks = len(chunks)
+        self.n_params = _lib.N_ORB[model] + 2 * _lib.NCOMP[model]
+        self.rank, self.world_size, self.group = rank, world_size, process_group
+        self.parts = lpt_partition([chunk_cost(len(ch["fl"])) for ch in chunks], world_size)
+        self.mine = sorted(self.parts[rank])
+        self._keep = []
+        self._host = []
+        descs = (_lib.PsoapChunk * max(1, len(self.mine)))()
+        Ns, nes = [], []
+        for k, idx in enumerate(self.mine):
+            ch = chunks[idx]
+            ep = ch["epoch"] if "epoch" in ch else epoch_index(ch["mask"])
+            host = dict(lwl=np.ascontiguousarray(ch["lwl"], dtype=np.float64),
+                        fl=np.ascontiguousarray(ch["fl"], dtype=np.float64),
+                        sigma=np.ascontiguousarray(np.asarray(ch["sigma"], dtype=np.float64) * soften),
+                        dates=np.ascontiguousarray(ch["date1D"], dtype=np.float64),
+                        epoch=np.ascontiguousarray(ep, dtype=np.int32))
+            N = len(host["fl"])
+            if not (len(host["lwl"]) == len(host["sigma"]) == len(host["epoch"]) == N):
+                raise ValueError("chunk %d: lwl, fl, sigma and the mask must select the same number of pixels" % idx)
+            dev = {k2: torch.from_numpy(v).pin_memory().cuda(non_blocking=True) for k2, v in host.items()}
+            self._host.append({k2: torch.from_numpy(v).pin_memory() for k2, v in host.items()})
+            self._keep.append(dev)
+            d = descs[k]
+            d.N, d.n_epochs = N, len(host["dates"])
+            d.lwl, d.epoch, d.fl = dev["lwl"].data_ptr(), dev["epoch"].data_ptr(), dev["fl"].data_ptr()
+            d.sigma, d.dates = dev["sigma"].data_ptr(), dev["dates"].data_ptr()
+            Ns.append(N)
+            nes.append(d.n_epochs)
+        torch.cuda.synchronize()
+        self.Ns = Ns
+        self._farm = _lib.vp(None)
+        self._results = torch.zeros((max(1, len(self.mine)), 4), dtype=torch.float64, device="cuda")
+        self._p_dev = torch.zeros(self.n_params, dtype=torch.float64, device="cuda")
+        self._p_pin = torch.zeros(self.n_params, dtype=torch.float64).pin_memory()
+        self._lnl_all = torch.zeros(self.n_chunks, dtype=torch.float64, device="cuda")
+        self._lnl_pin = torch.zeros(self.n_chunks, dtype=torch.float64).pin_memory()
+        self._mine_idx = torch.tensor(self.mine, dtype=torch.int64, device="cuda")
+        self.launches_per_eval = 0
+        if self.mine:
+            nb = max(1, min(nbranch, len(self.mine)))
+            nbytes = lib.psoap_farm_workspace_bytes(len(self.mine), (ctypes.c_int64 * len(Ns))(*Ns),
+                                                    (ctypes.c_int32 * len(nes))(*nes), nb)
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+            _lib.check(lib.psoap_farm_create(ctypes.byref(self._farm), _lib.MODELS[model], len(self.mine), descs, nb,
+                                             float(mu_GP), _lib.ptr(self._ws), nbytes))
+            self.launches_per_eval = lib.psoap_farm_launches_per_eval(self._farm)
+
+    # -- per-rank work --------------------------------------------------------------------------------
+    def flops_per_eval(self):
+        """Algorithmic flops of this rank's chunks: N^3/3 + 2 N^2 each."""
+        return float(sum(n ** 3 / 3.0 + 2.0 * n ** 2 for n in self.Ns))
+
+    def refresh_data(self):
+        """Re-upload this rank's chunk vectors from pinned host memory (bench.py's e2e leg)."""
+        nbytes = 0
+        for host, dev in zip(self._host, self._keep):
+            for k in host:
+                dev[k].copy_(host[k], non_blocking=True)
+                nbytes += host[k].numel() * host[k].element_size()
+        return nbytes
+
+    def lnprob_device(self, p_dev):
+        """Evaluate this rank's chunks for the device parameter vector p_dev (full registered vector, orbital
+        then GP, utils.py:4-8).  Asynchronous; returns the [n_mine, 4] result tensor (lnlike, logdet, quad, info)."""
+        if self.mine:
+            _lib.check(_lib.load().psoap_farm_lnprob(self._farm, _lib.ptr(p_dev), _lib.ptr(self._results),
+                                                     _lib.stream_ptr()))
+        return self._results
+
+    def chunk_lnlikes(self, p):
+        """All chunks' log-likelihoods for host parameter vector p, as a device tensor [n_chunks] (after the
+        cross-rank all-reduce when world_size > 1)."""
+        torch = _lib.torch_cuda()
+        p = np.asarray(p, dtype=np.float64)
+        if p.shape != (self.n_params,):
+            raise ValueError("p must hold the %d registered parameters of %s" % (self.n_params, self.model))
+        self._p_pin.copy_(torch.from_numpy(p))
+        self._p_dev.copy_(self._p_pin, non_blocking=True)
+        res = self.lnprob_device(self._p_dev)
+        self._lnl_all.zero_()
+        if self.mine:
+            self._lnl_all.index_copy_(0, self._mine_idx, res[:len(self.mine), 0])
+        if self.world_size > 1:
+            self._allreduce(self._lnl_all)
+        return self._lnl_all
+
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        # -inf entries are legal values here; SUM keeps them (-inf + 0 = -inf) exactly like np.sum does
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def lnprob(self, p):
+        """sample_parallel.py:371-390 without the prior: sum over chunks, in chunk order, of the per-chunk lnlike."""
+        lnl = self.chunk_lnlikes(p)
+        self._lnl_pin.copy_(lnl, non_blocking=False)
+        return float(np.sum(self._lnl_pin.numpy()))
+
+    def close(self):
+        if self._farm:
+            _lib.load().psoap_farm_destroy(self._farm)
+            self._farm = _lib.vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def combine_chunk_lnlikes(per_rank_vectors):
+    """Host-side statement of the cross-rank reduction (used by the gloo tests): element-wise sum of vectors
+    that are zero outside each rank's own chunks, then np.sum in chunk order."""
+    total = np.zeros_like(per_rank_vectors[0])
+    for v in per_rank_vectors:
+        total = total + v
+    return float(np.sum(total)), total

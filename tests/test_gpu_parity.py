@@ -1,0 +1,298 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the package / C ABI, against the golden vectors of
+the unmodified reference and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): covariance entries 1e-12 relative (+1e-300 absolute floor for entries in
+exp's denormal range) on bit-identical ln-wavelength inputs; lnlike 1e-10 relative.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import rel_close
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_RTOL, ENTRY_FLOOR = 1e-12, 1e-300
+LNLIKE_RTOL = 1e-10
+N_ORB = {"SB1": 6, "SB2": 7, "ST1": 11, "ST2": 12, "ST3": 13}
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------- fills
+def test_fill_golden(golden, torch_cuda):
+    from psoap_b200 import matrix_functions as mf
+    g = golden["fills"]
+    lw, lwp, amp, l = g["lwl"], g["lwl_predict"], g["amp"], g["l"]
+    N, M = lw.shape[1], len(lwp)
+    m = np.empty((N, N)); mf.fill_V11_f(m, lw[0], amp[0], l[0])
+    assert rel_close(m, g["V11_f"], ENTRY_RTOL, ENTRY_FLOOR)
+    m = np.empty((N, N)); mf.fill_V11_f_g(m, lw[0], lw[1], amp[0], l[0], amp[1], l[1])
+    assert rel_close(m, g["V11_f_g"], ENTRY_RTOL, ENTRY_FLOOR)
+    m = np.empty((N, N)); mf.fill_V11_f_g_h(m, lw[0], lw[1], lw[2], amp[0], l[0], amp[1], l[1], amp[2], l[2])
+    assert rel_close(m, g["V11_f_g_h"], ENTRY_RTOL, ENTRY_FLOOR)
+    assert np.array_equal(m, m.T) and np.array_equal(np.diag(m), np.diag(g["V11_f_g_h"]))
+    m = np.empty((N, M)); mf.fill_V12_f(m, lw[0], lwp, amp[0], l[0])
+    assert rel_close(m, g["V12_f"], ENTRY_RTOL, ENTRY_FLOOR)
+    m = np.empty((33, 33)); mf.fill_V11_f(m, g["far_lwl"], 0.5, 5.0)
+    assert rel_close(m, g["far_V11_f"], ENTRY_RTOL, ENTRY_FLOOR)
+
+
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 257, 1000])
+def test_fill_vs_oracle_ragged_sizes(N, oracle, torch_cuda):
+    from psoap_b200 import matrix_functions as mf
+    rng = np.random.default_rng(N)
+    lw = np.log(5100.0) + rng.uniform(0, 500.0, size=(3, N)) / oracle.c_kms
+    ref = np.empty((N, N)); oracle.fill_V11_f_g_h(ref, lw[0], lw[1], lw[2], 0.1, 5.0, 0.05, 7.0, 0.03, 6.0)
+    got = np.empty((N, N)); mf.fill_V11_f_g_h(got, lw[0], lw[1], lw[2], 0.1, 5.0, 0.05, 7.0, 0.03, 6.0)
+    assert rel_close(got, ref, ENTRY_RTOL, ENTRY_FLOOR)
+    # device tensor, strided view (ld > N), in place
+    big = torch_cuda.full((N + 3, N + 5), -7.0, dtype=torch_cuda.float64, device="cuda")
+    mf.fill_V11_f_g(big[:N, :N], lw[0], lw[1], 0.1, 5.0, 0.05, 7.0)
+    ref2 = np.empty((N, N)); oracle.fill_V11_f_g(ref2, lw[0], lw[1], 0.1, 5.0, 0.05, 7.0)
+    assert rel_close(big[:N, :N].cpu().numpy(), ref2, ENTRY_RTOL, ENTRY_FLOOR)
+    assert (big[N:, :] == -7.0).all() and (big[:, N:] == -7.0).all()  # nothing outside the view is touched
+    M = max(1, N // 2 + 1)
+    lwp = np.log(5100.0) + rng.uniform(0, 500.0, size=M) / oracle.c_kms
+    ref3 = np.empty((N, M)); oracle.fill_V12_f(ref3, lw[0], lwp, 0.2, 4.0)
+    got3 = np.empty((N, M)); mf.fill_V12_f(got3, lw[0], lwp, 0.2, 4.0)
+    assert rel_close(got3, ref3, ENTRY_RTOL, ENTRY_FLOOR)
+
+
+def test_fill_rejects_wrong_dtype(torch_cuda):
+    from psoap_b200 import matrix_functions as mf
+    with pytest.raises(ValueError):
+        mf.fill_V11_f(np.empty((4, 4), dtype=np.float32), np.zeros(4), 0.1, 5.0)
+
+
+# ---------------------------------------------------------------------------------------------- orbit / shift
+def test_orbit_golden(golden, torch_cuda):
+    from psoap_b200 import orbit
+    g = golden["orbits"]
+    dates = g["dates"]
+    for k in [k[:-2] for k in g.files if k.endswith("_p")]:
+        model = k.split("_")[0]
+        v = orbit.models[model](*g[k + "_p"], dates).get_velocities()
+        assert v.shape == g[k + "_v"].shape
+        # the reference's fsolve lands within ~3e-13 rad of the Kepler root
+        assert np.all(np.abs(v - g[k + "_v"]) <= 1e-10 * np.abs(g[k + "_v"]) + 1e-10), k
+    o = orbit.SB2(q=0.2, K=5.0, e=0.2, omega=10.0, P=10.0, T0=0.0, gamma=5.0, obs_dates=dates)
+    assert np.all(np.abs(o.get_velocities() - g["SB2_0_v"]) <= 1e-10)
+    with pytest.raises(AssertionError):
+        orbit.SB1(5.0, 1.2, 10.0, 10.0, 0.0, 5.0)
+
+
+def test_replicate_wls_bit_exact(golden, torch_cuda):
+    from psoap_b200 import data
+    g = golden["lnlike"]
+    for k in range(4):
+        pre = f"case{k}_"
+        out = data.replicate_wls(g[pre + "lwl"], g[pre + "vel"], g[pre + "mask"])
+        assert np.array_equal(out, g[pre + "lwls"])
+
+
+# ---------------------------------------------------------------------------------------------- lnlike
+def test_lnlike_golden(golden, torch_cuda):
+    from psoap_b200 import covariance
+    g = golden["lnlike"]
+    for k in range(4):
+        pre = f"case{k}_"
+        model = str(g[pre + "model"])
+        pg = g[pre + "p"][N_ORB[model]:]
+        lwls, fl, sigma = g[pre + "lwls"], g[pre + "fl"], g[pre + "sigma"]
+        N = len(fl)
+        V11 = np.empty((N, N))
+        got = covariance.lnlike[model](V11, *lwls, fl, sigma, *pg)
+        assert rel_close(got, g[pre + "lnlike"], LNLIKE_RTOL), (k, got, float(g[pre + "lnlike"]))
+        got = covariance.lnlike[model](V11, *lwls, fl, sigma, *pg, mu_GP=0.9)
+        assert rel_close(got, g[pre + "lnlike_mu09"], LNLIKE_RTOL)
+        pn = pg.copy(); pn[0] = -0.1
+        assert covariance.lnlike[model](V11, *lwls, fl, sigma, *pn) == -np.inf
+        lw2 = lwls.copy(); lw2[:, 1] = lw2[:, 0]
+        assert covariance.lnlike[model](V11, *lw2, fl, np.zeros_like(sigma), *pg) == -np.inf  # not PD
+        # C ABI host-buffer entry
+        got = covariance.lnlike_host(list(lwls), fl, sigma, pg[0::2], pg[1::2])
+        assert rel_close(got, g[pre + "lnlike"], LNLIKE_RTOL)
+
+
+@pytest.mark.parametrize("model,n_epochs,n_pix,mask_frac", [("SB1", 7, 100, 0.0), ("SB2", 10, 128, 0.0),
+                                                            ("SB2", 9, 150, 0.02), ("ST3", 8, 161, 0.05),
+                                                            ("SB2", 1, 1, 0.0), ("SB2", 3, 43, 0.0)])
+def test_lnlike_vs_oracle(model, n_epochs, n_pix, mask_frac, oracle, torch_cuda):
+    from psoap_b200 import covariance, synthetic
+    ch = synthetic.make_chunk(model, n_epochs, n_pix, seed=n_pix, mask_frac=mask_frac)
+    p = synthetic.default_params(model)
+    vel = oracle.get_velocities(model, p[:N_ORB[model]], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    V11 = np.empty((ch["N"], ch["N"]))
+    ref = oracle.lnlike[model](V11, *lwls, ch["fl"], ch["sigma"], *p[N_ORB[model]:])
+    got = covariance.lnlike[model](None, *lwls, ch["fl"], ch["sigma"], *p[N_ORB[model]:])
+    assert rel_close(got, ref, LNLIKE_RTOL), (got, ref)
+    # device-resident inputs give the same value
+    t = torch_cuda
+    got_dev = covariance.lnlike[model](None, *[t.from_numpy(x).cuda() for x in lwls], t.from_numpy(ch["fl"]).cuda(),
+                                       t.from_numpy(ch["sigma"]).cuda(), *p[N_ORB[model]:])
+    assert got_dev == got
+
+
+def test_lnlike_materialize_v11(oracle, torch_cuda):
+    from psoap_b200 import covariance, synthetic
+    ch = synthetic.make_chunk("SB2", 4, 50, seed=3)
+    p = synthetic.default_params("SB2")
+    vel = oracle.get_velocities("SB2", p[:7], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    V11 = np.empty((ch["N"], ch["N"]))
+    covariance.MATERIALIZE_V11 = True
+    try:
+        covariance.lnlike_f_g(V11, lwls[0], lwls[1], ch["fl"], ch["sigma"], *p[7:])
+    finally:
+        covariance.MATERIALIZE_V11 = False
+    ref = np.empty_like(V11); oracle.fill_V11_f_g(ref, lwls[0], lwls[1], *p[7:])
+    ref[np.diag_indices_from(ref)] += ch["sigma"] ** 2
+    assert rel_close(V11, ref, ENTRY_RTOL, ENTRY_FLOOR)
+
+
+# ---------------------------------------------------------------------------------------------- predict
+def test_predict_golden(golden, torch_cuda):
+    from psoap_b200 import covariance
+    g = golden["predict"]
+    lwls, fl, sigma, lwp, amp, l = g["lwls"], g["fl"], g["sigma"], g["lwl_predict"], g["amp"], g["l"]
+
+    def close(mu, Sig, kmu, kS):
+        scale = np.abs(g[kS]).max()
+        assert np.all(np.abs(mu - g[kmu]) <= 1e-9 * np.maximum(1.0, np.abs(g[kmu]))), kmu
+        assert np.all(np.abs(Sig - g[kS]) <= 1e-9 * scale), kS
+        assert np.array_equal(Sig, Sig.T)
+
+    mu, Sig = covariance.predict_f_g(lwls[0], lwls[1], fl, sigma, lwp[0], lwp[1], 0.7, amp[0], l[0], 0.3, amp[1], l[1])
+    close(mu, Sig, "fg_mu", "fg_Sigma")
+    mu = covariance.predict_f_g(lwls[0], lwls[1], fl, sigma, lwp[0], lwp[1], 0.7, amp[0], l[0], 0.3, amp[1], l[1],
+                                get_Sigma=False)
+    assert np.all(np.abs(mu - g["fg_mu_only"]) <= 1e-9)
+    mu, Sig = covariance.predict_f_g_sum(lwls[0], lwls[1], fl, sigma, lwp[0], lwp[1], 1.0, amp[0], l[0], amp[1], l[1])
+    close(mu, Sig, "fgsum_mu", "fgsum_Sigma")
+    mu, Sig = covariance.predict_f_g_h(lwls[0], lwls[1], lwls[2], fl, sigma, lwp[0], lwp[1], lwp[2], 0.5, 0.3, 0.2,
+                                       amp[0], l[0], amp[1], l[1], amp[2], l[2])
+    close(mu, Sig, "fgh_mu", "fgh_Sigma")
+    mu, Sig = covariance.predict_f_g_h_sum(lwls[0], lwls[1], lwls[2], fl, sigma, lwls[0], lwls[1], lwls[2], 1.0,
+                                           amp[0], l[0], amp[1], l[1], amp[2], l[2])
+    close(mu, Sig, "fghsum_mu", "fghsum_Sigma")
+    with pytest.raises(ValueError):  # covariance.py:294: V12.T only conforms when M == N
+        covariance.predict_f_g_h_sum(lwls[0], lwls[1], lwls[2], fl, sigma, lwp[0], lwp[1], lwp[2], 1.0, amp[0], l[0],
+                                     amp[1], l[1], amp[2], l[2])
+
+
+def test_predict_f_vs_oracle(oracle, torch_cuda):
+    from psoap_b200 import covariance, synthetic
+    ch = synthetic.make_chunk("SB1", 3, 90, seed=9)
+    grid = np.linspace(ch["lwl"].min(), ch["lwl"].max(), 140)
+    mu_r, S_r = oracle.predict_f(ch["lwl"], ch["fl"], ch["sigma"], grid, 0.1, 5.0, mu_GP=1.0)
+    mu, S = covariance.predict_f(ch["lwl"], ch["fl"], ch["sigma"], grid, 0.1, 5.0, mu_GP=1.0)
+    assert np.all(np.abs(mu - mu_r) <= 1e-9) and np.all(np.abs(S - S_r) <= 1e-9 * np.abs(S_r).max())
+
+
+# ---------------------------------------------------------------------------------------------- farm
+def test_farm_vs_oracle(oracle, torch_cuda):
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import ChunkFarm
+    specs = [(5, 60, 0.0), (6, 45, 0.03), (4, 128, 0.0), (7, 33, 0.1), (5, 77, 0.0), (3, 20, 0.0), (6, 64, 0.0)]
+    for model in ("SB2", "ST3", "SB1"):
+        chunks = [synthetic.make_chunk(model, ne, npx, seed=100 + i, mask_frac=mf, wl0=5000.0 + 3 * i)
+                  for i, (ne, npx, mf) in enumerate(specs)]
+        p = synthetic.default_params(model)
+        farm = ChunkFarm(model, chunks, nbranch=3)
+        total_ref, per_ref = oracle.farm_lnprob(model, p, chunks)
+        lnl = farm.chunk_lnlikes(p).cpu().numpy()
+        assert rel_close(lnl, per_ref, LNLIKE_RTOL), (model, lnl, per_ref)
+        assert rel_close(farm.lnprob(p), total_ref, LNLIKE_RTOL)
+        # second proposal through the same graph
+        p2 = p.copy(); p2[1 if model != "SB1" else 0] *= 1.3; p2[-1] *= 0.9
+        total_ref2, _ = oracle.farm_lnprob(model, p2, chunks)
+        assert rel_close(farm.lnprob(p2), total_ref2, LNLIKE_RTOL)
+        # sentinels: |v| >= c (sample_parallel.py:186-187) and negative hyper-parameters -> -inf
+        p3 = p.copy(); p3[1 if model != "SB1" else 0] = 4e5
+        assert farm.lnprob(p3) == -np.inf and oracle.farm_lnprob(model, p3, chunks)[0] == -np.inf
+        p4 = p.copy(); p4[-2] = -0.01
+        assert farm.lnprob(p4) == -np.inf
+        assert rel_close(farm.lnprob(p), total_ref, LNLIKE_RTOL)  # and the farm recovers afterwards
+        farm.close()
+
+
+def test_farm_partition_matches_single(oracle, torch_cuda):
+    """Emulated ranks on one GPU: the per-rank vectors (zero outside own chunks) sum to the single-rank answer."""
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import ChunkFarm, combine_chunk_lnlikes
+    chunks = [synthetic.make_chunk("SB2", 4, 30 + 7 * i, seed=300 + i) for i in range(9)]
+    p = synthetic.default_params("SB2")
+    single = ChunkFarm("SB2", chunks)
+    ref_vec = single.chunk_lnlikes(p).cpu().numpy().copy()
+    vecs = []
+    for r in range(4):
+        f = ChunkFarm("SB2", chunks, rank=r, world_size=4)
+        f.world_size = 1  # no process group here: take the un-reduced vector
+        vecs.append(f.chunk_lnlikes(p).cpu().numpy().copy())
+        f.close()
+    total, vec = combine_chunk_lnlikes(vecs)
+    assert np.array_equal(vec, ref_vec)
+    assert total == float(np.sum(ref_vec))
+    single.close()
+
+
+# ---------------------------------------------------------------------------------------------- full size
+def _torch_reference_lnlike(torch, lwls, fl, sigma, pg, mu=1.0):
+    """Independent full-size check: our operator-surface fill + cuSOLVER Cholesky through torch."""
+    from psoap_b200 import matrix_functions as mf
+    N = len(fl)
+    K = torch.empty((N, N), dtype=torch.float64, device="cuda")
+    fills = {1: mf.fill_V11_f, 2: mf.fill_V11_f_g, 3: mf.fill_V11_f_g_h}
+    fills[len(lwls)](K, *lwls, *pg)
+    K.diagonal().add_(torch.from_numpy(sigma).cuda() ** 2)
+    L = torch.linalg.cholesky(K)
+    r = (torch.from_numpy(fl).cuda() - mu)[:, None]
+    y = torch.linalg.solve_triangular(L, r, upper=False)
+    logdet = 2.0 * torch.log(torch.diagonal(L)).sum()
+    return float(-0.5 * ((y * y).sum() + logdet))
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
+def test_full_size_configs(cfg, oracle, torch_cuda):
+    """BASELINE.json configs at full size: agreement with an independent GPU factorisation (cuSOLVER via torch)
+    and invariance under a random permutation of the pixels (a different elimination order)."""
+    from psoap_b200 import covariance, synthetic
+    model, chunks = synthetic.config_chunks(cfg)
+    ch = chunks[0]
+    p = synthetic.default_params(model)
+    vel = oracle.get_velocities(model, p[:N_ORB[model]], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    pg = p[N_ORB[model]:]
+    got = covariance.lnlike[model](None, *lwls, ch["fl"], ch["sigma"], *pg)
+    ref = _torch_reference_lnlike(torch_cuda, list(lwls), ch["fl"], ch["sigma"], pg)
+    assert np.isfinite(got) and rel_close(got, ref, LNLIKE_RTOL), (got, ref)
+    perm = np.random.default_rng(1).permutation(ch["N"])
+    got_p = covariance.lnlike[model](None, *[x[perm] for x in lwls], ch["fl"][perm], ch["sigma"][perm], *pg)
+    assert rel_close(got_p, got, LNLIKE_RTOL), (got_p, got)
+
+
+def test_block_additivity(oracle, torch_cuda):
+    """Two pixel sets far apart in wavelength have exactly zero cross-covariance (exp underflow), so the joint
+    log-likelihood is the sum of the parts."""
+    from psoap_b200 import covariance, synthetic
+    a = synthetic.make_chunk("SB2", 6, 200, seed=21, wl0=5000.0)
+    b = synthetic.make_chunk("SB2", 5, 333, seed=22, wl0=5400.0)
+    p = synthetic.default_params("SB2")
+    parts, lw_all = [], []
+    for ch in (a, b):
+        vel = oracle.get_velocities("SB2", p[:7], ch["date1D"])
+        lw = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+        lw_all.append(lw)
+        parts.append(covariance.lnlike_f_g(None, lw[0], lw[1], ch["fl"], ch["sigma"], *p[7:]))
+    lw = np.concatenate(lw_all, axis=1)
+    joint = covariance.lnlike_f_g(None, lw[0], lw[1], np.concatenate([a["fl"], b["fl"]]),
+                                  np.concatenate([a["sigma"], b["sigma"]]), *p[7:])
+    assert rel_close(joint, parts[0] + parts[1], LNLIKE_RTOL)

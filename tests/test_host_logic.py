@@ -1,0 +1,88 @@
+"""CPU: host-side logic — chunk partitioning, the cross-rank reduction (gloo, world_size 2), synthetic inputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_partition_covers_and_balances():
+    from psoap_b200.farm import chunk_cost, lpt_partition
+    Ns = [2000 + (4000 * i) // 255 for i in range(256)]
+    costs = [chunk_cost(n) for n in Ns]
+    for g in (1, 2, 4, 8):
+        parts = lpt_partition(costs, g)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(256))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / g) < 1.02  # LPT is within 2 % of perfect here
+        assert parts == lpt_partition(costs, g)      # deterministic
+
+
+def test_epoch_index_matches_mask_broadcast():
+    from psoap_b200.data import epoch_index
+    rng = np.random.default_rng(0)
+    mask = rng.uniform(size=(5, 17)) > 0.2
+    v = rng.normal(size=5)
+    expect = (v[:, np.newaxis] * np.ones_like(mask))[mask]  # psoap/data.py:61
+    assert np.array_equal(v[epoch_index(mask)], expect)
+
+
+def test_synthetic_chunks_are_seeded_and_shaped():
+    from psoap_b200 import synthetic
+    a = synthetic.make_chunk("SB2", 5, 40, seed=3, mask_frac=0.1)
+    b = synthetic.make_chunk("SB2", 5, 40, seed=3, mask_frac=0.1)
+    assert all(np.array_equal(a[k], b[k]) for k in ("lwl", "fl", "sigma", "mask", "date1D", "epoch"))
+    assert a["N"] == a["mask"].sum() == len(a["fl"]) < 200
+    model, chunks = synthetic.config_chunks("C4")
+    Ns = [c["N"] for c in chunks]
+    assert model == "SB2" and len(chunks) == 256 and min(Ns) == 2000 and max(Ns) == 6000
+    assert synthetic.config_chunks("C2")[1][0]["N"] == 9000
+
+
+def test_synthetic_velocities_match_oracle(oracle):
+    from psoap_b200 import synthetic
+    dates = np.linspace(-3.0, 70.0, 23)
+    for model in ("SB1", "SB2", "ST3"):
+        p = synthetic.ORBIT_PARAMS[model]
+        assert np.allclose(synthetic.host_velocities(model, p, dates), oracle.get_velocities(model, p, dates),
+                           rtol=0, atol=1e-10)
+
+
+def _worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import chunk_cost, lpt_partition
+    chunks = [synthetic.make_chunk("SB2", 3, 20 + 5 * i, seed=50 + i, mask_frac=0.05 * (i % 2)) for i in range(7)]
+    p = synthetic.default_params("SB2")
+    if os.environ.get("PSOAP_TEST_INF") == "1":
+        p[1] = 4e5  # |v| >= c on every chunk
+    parts = lpt_partition([chunk_cost(c["N"]) for c in chunks], world)
+    vec = torch.zeros(len(chunks), dtype=torch.float64)
+    for i in parts[rank]:
+        vec[i] = orc.chunk_lnprob("SB2", p, chunks[i])  # the oracle stands in for the GPU evaluation
+    dist.all_reduce(vec, op=dist.ReduceOp.SUM)         # the one collective of the path
+    total = float(np.sum(vec.numpy()))
+    ref_total, ref_vec = orc.farm_lnprob("SB2", p, chunks)
+    ok = np.array_equal(vec.numpy(), ref_vec) and total == ref_total
+    with open(os.path.join(tmp, f"rank{rank}.txt"), "w") as fh:
+        fh.write("ok" if ok else f"mismatch {total} {ref_total}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("inf_case", ["0", "1"])
+def test_two_rank_gloo_reduction_equals_serial_sum(tmp_path, inf_case):
+    import torch.multiprocessing as mp
+    os.environ["PSOAP_TEST_INF"] = inf_case
+    port = 29500 + (os.getpid() % 2000) + int(inf_case)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
