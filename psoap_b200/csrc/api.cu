@@ -534,6 +534,44 @@ int psoap_farm_destroy(psoap_farm* f) {
     return PSOAP_OK;
 }
 
+// Times the trailing-update kernel (syrk_kernel, the dominant kernel of the path) alone: `reps` launches of the
+// rank-128 update of an m x m lower triangle (m a multiple of 128), CUDA events on a private stream.
+// flops_per_launch is the algorithmic count 128 * m * (m + 128) (2 flops per multiply-add on the lower tiles).
+int psoap_bench_syrk(int64_t m, int reps, double* avg_ms_out, double* flops_per_launch_out) {
+    if (m < NB || m % NB || reps < 1 || !avg_ms_out) return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
+    int rc = set_kernel_attributes();
+    if (rc) return rc;
+    double *W = nullptr, *P = nullptr, *y = nullptr, *r = nullptr;
+    CUDA_TRY(cudaMalloc(&W, (size_t)m * m * 8));
+    CUDA_TRY(cudaMalloc(&P, (size_t)m * NB * 8));
+    CUDA_TRY(cudaMalloc(&y, NB * 8));
+    CUDA_TRY(cudaMalloc(&r, (size_t)m * 8));
+    CUDA_TRY(cudaMemset(W, 0, (size_t)m * m * 8));
+    CUDA_TRY(cudaMemset(y, 0, NB * 8));
+    CUDA_TRY(cudaMemset(r, 0, (size_t)m * 8));
+    std::vector<double> hp((size_t)m * NB);
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = 1e-3 * (double)((i * 2654435761u) % 1000) - 0.5;
+    CUDA_TRY(cudaMemcpy(P, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice));
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int R = (int)(m / NB), ntiles = R * (R + 1);
+    for (int w = 0; w < 2; ++w) { syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, m, -1, 0, P, m, ntiles, y, r); ++g_launches; }
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; ++i) { syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, m, -1, 0, P, m, ntiles, y, r); ++g_launches; }
+    cudaEventRecord(e1, st);
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    cudaFree(W); cudaFree(P); cudaFree(y); cudaFree(r);
+    *avg_ms_out = ms / reps;
+    if (flops_per_launch_out) *flops_per_launch_out = 128.0 * (double)m * (double)(m + NB);
+    return PSOAP_OK;
+}
+
 int psoap_fp64_peak_tflops(double* tflops_out) {
     if (!tflops_out) return fail(PSOAP_ERR_ARG, "psoap_fp64_peak_tflops: null");
     int dev = 0, sms = 0;

@@ -115,22 +115,26 @@ class ChunkFarm:
                                                      _lib.stream_ptr()))
         return self._results
 
-    def chunk_lnlikes(self, p):
-        """All chunks' log-likelihoods for host parameter vector p, as a device tensor [n_chunks] (after the
-        cross-rank all-reduce when world_size > 1)."""
-        torch = _lib.torch_cuda()
-        p = np.asarray(p, dtype=np.float64)
-        if p.shape != (self.n_params,):
-            raise ValueError("p must hold the %d registered parameters of %s" % (self.n_params, self.model))
-        self._p_pin.copy_(torch.from_numpy(p))
-        self._p_dev.copy_(self._p_pin, non_blocking=True)
-        res = self.lnprob_device(self._p_dev)
+    def chunk_lnlikes_device(self, p_dev):
+        """All chunks' log-likelihoods for a DEVICE parameter vector, as a device tensor [n_chunks]; asynchronous
+        (no host synchronisation).  With world_size > 1 it ends with the one collective of the path."""
+        res = self.lnprob_device(p_dev)
         self._lnl_all.zero_()
         if self.mine:
             self._lnl_all.index_copy_(0, self._mine_idx, res[:len(self.mine), 0])
         if self.world_size > 1:
             self._allreduce(self._lnl_all)
         return self._lnl_all
+
+    def chunk_lnlikes(self, p):
+        """Same for a HOST parameter vector p (staged through pinned memory)."""
+        torch = _lib.torch_cuda()
+        p = np.asarray(p, dtype=np.float64)
+        if p.shape != (self.n_params,):
+            raise ValueError("p must hold the %d registered parameters of %s" % (self.n_params, self.model))
+        self._p_pin.copy_(torch.from_numpy(p))
+        self._p_dev.copy_(self._p_pin, non_blocking=True)
+        return self.chunk_lnlikes_device(self._p_dev)
 
     def _allreduce(self, t):
         import torch.distributed as dist

@@ -1,0 +1,14 @@
+"""Run the dominant kernel alone (for ncu captures): python tools/bench_syrk.py [m] [reps]"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from psoap_b200 import _lib  # noqa: E402
+
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+lib = _lib.load()
+ms, fl = ctypes.c_double(), ctypes.c_double()
+_lib.check(lib.psoap_bench_syrk(m, reps, ctypes.byref(ms), ctypes.byref(fl)))
+print("m=%d avg_ms=%.4f tflops=%.2f" % (m, ms.value, fl.value / ms.value * 1e-9))

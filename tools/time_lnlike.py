@@ -44,6 +44,10 @@ def time_chunk(model, n_epochs, n_pix, reps=5):
 
 
 if __name__ == "__main__":
+    if "--one" in sys.argv:  # python tools/time_lnlike.py --one SB2 20 200  (for ncu launch lists)
+        i = sys.argv.index("--one")
+        print(json.dumps(time_chunk(sys.argv[i + 1], int(sys.argv[i + 2]), int(sys.argv[i + 3]), reps=1)))
+        sys.exit(0)
     out = []
     for model, ne, npx in [("SB2", 20, 100), ("SB2", 20, 200), ("SB1", 20, 200), ("SB2", 20, 300), ("SB2", 30, 300),
                            ("ST3", 40, 250)] + ([("SB2", 64, 256)] if "--big" in sys.argv else []):
