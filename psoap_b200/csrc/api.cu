@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -15,6 +16,7 @@
 #include "chol.cuh"
 #include "common.cuh"
 #include "fill.cuh"
+#include "gemm.cuh"
 #include "orbit.cuh"
 
 using namespace psoap;
@@ -46,13 +48,18 @@ inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
 
 std::once_flag g_attr_once;
 int g_attr_status = 0;
+int g_num_sms = 148;
+inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, 2 * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int dev = 0;
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         g_attr_status = (int)e;
     });
     if (g_attr_status != 0)
@@ -98,25 +105,62 @@ void carve_factor_ws(char* base, int64_t Nt, FactorWs* ws, bool with_W) {
     ws->info = (int*)take(2 * 4);
 }
 
+// Streams of one factorisation pipeline: the caller's stream plus a high-priority side stream on which the next
+// panel is factored while the bulk of the current trailing update runs (look-ahead).
+struct Lanes {
+    cudaStream_t main;
+    cudaStream_t side;   // may be null: no look-ahead
+    cudaEvent_t e1, e2;
+};
+
 // Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
 // (T_elim == T_total: plain Cholesky).  The trailing block is left holding the Schur complement.
-int launch_factor(cudaStream_t st, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
+int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
                   const int* sentinel, double* result) {
-    for (int kb = 0; kb < T_elim; ++kb) {
-        const int is_last = (kb == T_elim - 1);
-        const int kbeg = (kb == 0) ? (pad / BK) * BK : 0;
-        double* P = ws.P[kb & 1];
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
-                                                      ws.info, sentinel, is_last, result);
-        LAUNCH_CHECK();
+    cudaStream_t st = ln.main;
+    auto potrf = [&](cudaStream_t s, int kb) {
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
+                                                     ws.info, sentinel, kb == T_elim - 1, result);
+    };
+    auto trsm = [&](cudaStream_t s, int kb) {
         const int R = T_total - kb - 1;
-        if (R <= 0) continue;
-        trsm_kernel<<<2 * R, 256, GEMM_SMEM, st>>>(W, ld, kb, kbeg, ws.Linv, P, ws.Nt);
-        LAUNCH_CHECK();
-        const int ntiles = R * (R + 1);
-        syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, ld, kb, kbeg, P, ws.Nt, ntiles, ws.y + (int64_t)kb * NB,
-                                                        ws.rvec);
-        LAUNCH_CHECK();
+        TrsmSrc src;
+        src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
+        src.Linv = ws.Linv; src.P = ws.P[kb & 1]; src.ldp = ws.Nt;
+        trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
+    };
+    auto syrk = [&](cudaStream_t s, int kb, int part) {
+        const int R = T_total - kb - 1;
+        SyrkSrc src;
+        src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
+        src.P = ws.P[kb & 1]; src.ldp = ws.Nt; src.part = part;
+        const int ntiles = part == 0 ? R * (R + 1) : (part == 1 ? 2 * R : R * (R - 1));
+        const int nres = part == 2 ? 0 : R;
+        const int nctas = persistent_ctas(ntiles);
+        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, ws.y + (int64_t)kb * NB, ws.rvec);
+    };
+    potrf(st, 0);
+    LAUNCH_CHECK();
+    if (T_total > 1) { trsm(st, 0); LAUNCH_CHECK(); }
+    for (int kb = 0; kb < T_elim; ++kb) {
+        const int R = T_total - kb - 1;
+        if (R <= 0) break;
+        const bool next = kb + 1 < T_elim;
+        if (!next) { syrk(st, kb, 0); LAUNCH_CHECK(); break; }
+        if (ln.side == nullptr) {
+            syrk(st, kb, 0); LAUNCH_CHECK();
+            potrf(st, kb + 1); LAUNCH_CHECK();
+            if (R > 1) { trsm(st, kb + 1); LAUNCH_CHECK(); }
+            continue;
+        }
+        syrk(st, kb, 1); LAUNCH_CHECK();
+        CUDA_TRY(cudaEventRecord(ln.e1, st));
+        CUDA_TRY(cudaStreamWaitEvent(ln.side, ln.e1, 0));
+        potrf(ln.side, kb + 1); LAUNCH_CHECK();
+        if (R > 1) { trsm(ln.side, kb + 1); LAUNCH_CHECK(); }
+        CUDA_TRY(cudaEventRecord(ln.e2, ln.side));
+        if (R > 1) { syrk(st, kb, 2); LAUNCH_CHECK(); }
+        CUDA_TRY(cudaStreamWaitEvent(st, ln.e2, 0));
     }
     return PSOAP_OK;
 }
@@ -138,14 +182,34 @@ int launch_fill_lower(int ncomp, cudaStream_t st, double* W, int64_t ld, int T, 
 }
 
 // fill + factor + fused solve of one chunk on stream st
-int launch_chunk(cudaStream_t st, int ncomp, int64_t N, const ZSource& zs, const double* fl, const double* sigma,
+int launch_chunk(const Lanes& ln, int ncomp, int64_t N, const ZSource& zs, const double* fl, const double* sigma,
                  double mu, const GpParams& gp, const FactorWs& ws, const int* sentinel, double* result) {
     const int64_t Np = padded_dim(N);
     const int T = (int)(Np / NB);
     const int pad = (int)(Np - N);
-    int rc = launch_fill_lower(ncomp, st, ws.W, Np, T, pad, zs, sigma, fl, mu, gp, ws);
+    int rc = launch_fill_lower(ncomp, ln.main, ws.W, Np, T, pad, zs, sigma, fl, mu, gp, ws);
     if (rc) return rc;
-    return launch_factor(st, ws.W, Np, T, T, pad, ws, sentinel, result);
+    return launch_factor(ln, ws.W, Np, T, T, pad, ws, sentinel, result);
+}
+
+// Side stream + events for calls on a caller-provided stream (one set per host thread).
+struct SideLane {
+    cudaStream_t side = nullptr;
+    cudaEvent_t e1 = nullptr, e2 = nullptr;
+};
+int get_lanes(cudaStream_t user, Lanes* ln) {
+    thread_local SideLane sl;
+    if (!sl.side) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&sl.side, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.e1, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.e2, cudaEventDisableTiming));
+    }
+    const char* la_env = getenv("PSOAP_LOOKAHEAD");
+    const bool lookahead = la_env ? (atoi(la_env) != 0) : true;
+    ln->main = user; ln->side = lookahead ? sl.side : nullptr; ln->e1 = sl.e1; ln->e2 = sl.e2;
+    return PSOAP_OK;
 }
 
 __global__ void write_result_kernel(double* result, double lnlike, double logdet, double quad, double info) {
@@ -278,7 +342,10 @@ int psoap_lnlike(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g,
     if (rc) return rc;
     FactorWs ws;
     carve_factor_ws((char*)workspace, padded_dim(N), &ws, true);
-    return launch_chunk(st, ncomp, N, direct_z(lwl_f, lwl_g, lwl_h), fl, sigma, mu_GP, gp, ws, nullptr, (double*)result);
+    Lanes ln;
+    rc = get_lanes(st, &ln);
+    if (rc) return rc;
+    return launch_chunk(ln, ncomp, N, direct_z(lwl_f, lwl_g, lwl_h), fl, sigma, mu_GP, gp, ws, nullptr, (double*)result);
 }
 
 namespace {
@@ -343,8 +410,10 @@ int psoap_schur(double* S, int64_t ld, int64_t n, int64_t m, void* workspace, si
     if (rc) return rc;
     FactorWs ws;
     carve_factor_ws((char*)workspace, Nt, &ws, false);
-    return launch_factor((cudaStream_t)stream, S, ld, (int)(Nn / NB), (int)(Nt / NB), (int)(Nn - n), ws, nullptr,
-                         (double*)result);
+    Lanes ln;
+    rc = get_lanes((cudaStream_t)stream, &ln);
+    if (rc) return rc;
+    return launch_factor(ln, S, ld, (int)(Nn / NB), (int)(Nt / NB), (int)(Nn - n), ws, nullptr, (double*)result);
 }
 
 }  // extern "C"
@@ -378,7 +447,9 @@ struct psoap_farm {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     std::vector<cudaStream_t> streams;
+    std::vector<cudaStream_t> side_streams;
     std::vector<cudaEvent_t> events;
+    std::vector<cudaEvent_t> side_events;
     int launches = 0;
 };
 
@@ -473,6 +544,14 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
     f->events.resize(nbranch + 1);
     for (auto& s : f->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     for (auto& ev : f->events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    f->side_streams.resize(nbranch);
+    f->side_events.resize(2 * nbranch);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (auto& s : f->side_streams) cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi);
+        for (auto& ev : f->side_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    }
     cudaStream_t s0 = f->streams[nbranch];
     const int64_t before = g_launches.load();
     e = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
@@ -484,6 +563,8 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
     gp.dev = f->p_buf + f->norb;
     for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
     rc = PSOAP_OK;
+    const char* la_env = getenv("PSOAP_FARM_LOOKAHEAD");
+    const bool lookahead = la_env ? (atoi(la_env) != 0) : true;
     for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
         cudaStream_t sb = f->streams[b];
         cudaStreamWaitEvent(sb, f->events[nbranch], 0);
@@ -494,7 +575,11 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
             zs.epoch = ch.epoch; zs.vel = hd[idx].vel; zs.n_epochs = ch.n_epochs; zs.shift = 1;
             FactorWs ws = f->branch_ws[b];
             ws.Nt = padded_dim(ch.N);
-            rc = launch_chunk(sb, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + idx, f->results + 4 * idx);
+            Lanes ln;
+            ln.main = sb;
+            ln.side = lookahead ? f->side_streams[b] : nullptr;
+            ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
+            rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + idx, f->results + 4 * idx);
             if (rc) break;
         }
         cudaEventRecord(f->events[b], sb);
@@ -529,7 +614,9 @@ int psoap_farm_destroy(psoap_farm* f) {
     if (f->exec) cudaGraphExecDestroy(f->exec);
     if (f->graph) cudaGraphDestroy(f->graph);
     for (auto& s : f->streams) if (s) cudaStreamDestroy(s);
+    for (auto& s : f->side_streams) if (s) cudaStreamDestroy(s);
     for (auto& ev : f->events) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : f->side_events) if (ev) cudaEventDestroy(ev);
     delete f;
     return PSOAP_OK;
 }
@@ -558,9 +645,12 @@ int psoap_bench_syrk(int64_t m, int reps, double* avg_ms_out, double* flops_per_
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
     const int R = (int)(m / NB), ntiles = R * (R + 1);
-    for (int w = 0; w < 2; ++w) { syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, m, -1, 0, P, m, ntiles, y, r); ++g_launches; }
+    SyrkSrc src;
+    src.W = W; src.ld = m; src.kb = -1; src.kbeg = 0; src.P = P; src.ldp = m; src.part = 0;
+    const int nctas = persistent_ctas(ntiles);
+    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r); ++g_launches; }
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; ++i) { syrk_kernel<<<ntiles + R, 256, GEMM_SMEM, st>>>(W, m, -1, 0, P, m, ntiles, y, r); ++g_launches; }
+    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r); ++g_launches; }
     cudaEventRecord(e1, st);
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;

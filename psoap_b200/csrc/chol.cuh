@@ -5,8 +5,8 @@
 //   for kb = 0 .. T-1
 //     potrf_diag : one CTA factors the 128x128 diagonal block in registers, builds L_kk^-1 alongside
 //                  (Gauss-Jordan), y_k = L_kk^-1 r_k, logdet += sum log d_j, quad += |y_k|^2
-//     trsm       : P[i, :] = W[i, kb-panel] * L_kk^-T for the rows below, as a DMMA GEMM with L_kk^-1
-//     syrk       : W[I, J] -= P_I P_J^T on the trailing lower triangle (DMMA), plus r_I -= P_I y_k
+//     trsm       : P[i, :] = W[i, kb-panel] * L_kk^-T for the rows below, as a DMMA GEMM with L_kk^-1 (gemm.cuh)
+//     syrk       : W[I, J] -= P_I P_J^T on the trailing lower triangle (DMMA), plus r_I -= P_I y_k (gemm.cuh)
 // The factor itself is never needed by the likelihood, so the panel P lives in a small (L2-resident)
 // ping-pong buffer and is not written back.
 #pragma once
@@ -164,178 +164,6 @@ potrf_diag_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, dou
             result[2] = acc[2];
             result[3] = (double)inf;
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// DMMA tile GEMM  acc[i][j] = sum_{k in [kbeg,kend)} Ai[i,k] * Bj[j,k]   (128 x 64 tile, 256 threads)
-//   Ai, Bj column-major (row index contiguous).  cp.async 16 B, 4 stages of BK = 16, padded shared rows
-//   (stride = rows + 4 doubles) so the m8n8k4 fragment loads are bank-conflict free.
-//   mma M <-> j, mma N <-> i, so each thread ends up with two consecutive rows i of a column j
-//   (double2 epilogue on the column-major output).  2 CTAs per SM: one CTA's epilogue (HBM read-modify-
-//   write of its tile) overlaps the other's main loop.
-// ------------------------------------------------------------------------------------------------------
-constexpr int BI = 128, BJ = 64, BK = 16, STAGES = 4;
-constexpr int SA = BI + 4, SB = BJ + 4;
-constexpr int STAGE_DOUBLES = BK * SA + BK * SB;
-constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8;
-
-struct GemmTile {
-    const double* Ai;
-    int64_t lda;
-    const double* Bj;
-    int64_t ldb;
-    int kbeg, kend;
-    double* C;
-    int64_t ldc;
-};
-
-template <int MODE>  // 0: C = acc, 1: C -= acc
-__device__ __forceinline__ void gemm_tile(const GemmTile& t, double* sm) {
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tq = lane & 3;
-    const int wi = warp & 3, wj = warp >> 2;
-    const int KT = (t.kend - t.kbeg) / BK;
-
-    auto load_stage = [&](int stage, int kt) {
-        double* sA = sm + stage * STAGE_DOUBLES;
-        double* sB = sA + BK * SA;
-        const int k0 = t.kbeg + kt * BK;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int q = tid + 256 * r;
-            const int col = q >> 6, row2 = q & 63;
-            cp_async16(sA + col * SA + 2 * row2, t.Ai + 2 * row2 + (int64_t)(k0 + col) * t.lda);
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int q = tid + 256 * r;
-            const int col = q >> 5, row2 = q & 31;
-            cp_async16(sB + col * SB + 2 * row2, t.Bj + 2 * row2 + (int64_t)(k0 + col) * t.ldb);
-        }
-    };
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const int nk = kt + STAGES - 1;
-        if (nk < KT) load_stage(nk % STAGES, nk);
-        cp_async_commit();
-        const double* sA = sm + (kt % STAGES) * STAGE_DOUBLES;
-        const double* sB = sA + BK * SA;
-#pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[4], b[4];
-#pragma unroll
-            for (int mj = 0; mj < 4; ++mj) a[mj] = sB[(kk * 4 + tq) * SB + wj * 32 + mj * 8 + g];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = sA[(kk * 4 + tq) * SA + wi * 32 + ni * 8 + g];
-#pragma unroll
-            for (int mj = 0; mj < 4; ++mj)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
-        }
-    }
-    cp_async_wait<0>();
-
-    if (MODE == 0) {
-#pragma unroll
-        for (int mj = 0; mj < 4; ++mj)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int i = wi * 32 + ni * 8 + tq * 2, j = wj * 32 + mj * 8 + g;
-                *reinterpret_cast<double2*>(t.C + i + (int64_t)j * t.ldc) = make_double2(acc[mj][ni][0], acc[mj][ni][1]);
-            }
-    } else {
-        double2 cv[4][4];
-#pragma unroll
-        for (int mj = 0; mj < 4; ++mj)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int i = wi * 32 + ni * 8 + tq * 2, j = wj * 32 + mj * 8 + g;
-                cv[mj][ni] = *reinterpret_cast<const double2*>(t.C + i + (int64_t)j * t.ldc);
-            }
-#pragma unroll
-        for (int mj = 0; mj < 4; ++mj)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int i = wi * 32 + ni * 8 + tq * 2, j = wj * 32 + mj * 8 + g;
-                cv[mj][ni].x -= acc[mj][ni][0];
-                cv[mj][ni].y -= acc[mj][ni][1];
-                *reinterpret_cast<double2*>(t.C + i + (int64_t)j * t.ldc) = cv[mj][ni];
-            }
-    }
-}
-
-// trsm: rows below panel kb.  Block t -> row tile I = kb+1 + t/2, column half jh = t%2.
-//   P[I*128 + :, jh*64 + :] = W[I*128 + :, kb*128 + (0..(jh+1)*64)] * Linv[jh*64 + :, same]^T
-// nrows_tiles counts 128-row tiles below the panel (border rows of a Schur problem included).
-__global__ void __launch_bounds__(256, 2)
-trsm_kernel(const double* __restrict__ W, int64_t ld, int kb, int kbeg, const double* __restrict__ Linv,
-            double* __restrict__ P, int64_t ldp) {
-    extern __shared__ double sm[];
-    const int t = blockIdx.x;
-    const int I = kb + 1 + (t >> 1), jh = t & 1;
-    GemmTile gt;
-    gt.Ai = W + (int64_t)I * NB + (int64_t)kb * NB * ld;
-    gt.lda = ld;
-    gt.Bj = Linv + jh * BJ;
-    gt.ldb = NB;
-    gt.kbeg = kbeg;
-    gt.kend = (jh + 1) * BJ;
-    gt.C = P + (int64_t)I * NB + (int64_t)jh * BJ * ldp;
-    gt.ldc = ldp;
-    gemm_tile<0>(gt, sm);
-}
-
-// syrk: trailing update with panel kb, rows/cols of tiles I in [kb+1, T).  Blocks [0, ntiles) are 128x64
-// tiles of the lower triangle (row r = I-kb-1 has 2(r+1) tiles); blocks [ntiles, ntiles + nrow) update the
-// residual r_I -= P_I y_k (deterministic two-half reduction).  jlimit: last tile column that needs
-// updating (T for the likelihood; Schur problems pass the full border).
-__global__ void __launch_bounds__(256, 2)
-syrk_kernel(double* __restrict__ W, int64_t ld, int kb, int kbeg, const double* __restrict__ P, int64_t ldp,
-            int ntiles, const double* __restrict__ yk, double* __restrict__ rvec) {
-    extern __shared__ double sm[];
-    const int t = blockIdx.x;
-    if (t < ntiles) {
-        int r = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((r + 1) * (r + 2) <= t) ++r;
-        while (r * (r + 1) > t) --r;
-        const int I = kb + 1 + r;
-        const int J64 = 2 * (kb + 1) + (t - r * (r + 1));
-        GemmTile gt;
-        gt.Ai = P + (int64_t)I * NB;
-        gt.lda = ldp;
-        gt.Bj = P + (int64_t)J64 * BJ;
-        gt.ldb = ldp;
-        gt.kbeg = kbeg;
-        gt.kend = NB;
-        gt.C = W + (int64_t)I * NB + (int64_t)J64 * BJ * ld;
-        gt.ldc = ld;
-        gemm_tile<1>(gt, sm);
-    } else {
-        const int I = kb + 1 + (t - ntiles);
-        const int tid = threadIdx.x;
-        const int row = tid & (NB - 1), half = tid >> 7;
-        const double* p = P + (int64_t)I * NB + row + (int64_t)half * 64 * ldp;
-        double s = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) s = fma(p[(int64_t)c * ldp], yk[half * 64 + c], s);
-        sm[tid] = s;
-        __syncthreads();
-        if (half == 0) rvec[I * NB + row] -= (sm[row] + sm[NB + row]);
     }
 }
 

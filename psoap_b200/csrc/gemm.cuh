@@ -1,0 +1,286 @@
+// gemm.cuh — persistent DMMA tile GEMM for the panel solve (trsm) and the trailing update (syrk).
+//
+//   acc[i][j] = sum_k Ai[i,k] * Bj[j,k]      128 x 64 output tile, 256 threads (8 warps, 32 x 32 each)
+//
+// B200-native structure:
+//   * operands are staged by the TMA engine: one cp.async.bulk (1-D bulk tensor copy, SASS UBLKCP) per matrix
+//     column segment, completing on an mbarrier with a transaction count; no thread moves operand data and
+//     there is no __syncthreads in the main loop.  Shared rows are padded (+4 doubles) so the m8n8k4 fragment
+//     loads are bank-conflict free.
+//   * producer duty is spread over the 8 warps (lane 0 of each issues the copies for 2 of the 16 k-columns of
+//     a stage), consumer release goes through a second set of mbarriers ("empty"), so warps drift freely and
+//     a stage is refilled one item after it was consumed.
+//   * CTAs are persistent (2 per SM) and the TMA pipeline runs ahead ACROSS tiles: the next tile's operands
+//     land while the current tile's epilogue (read-modify-write of C in HBM, prefetched into L2 at tile start)
+//     is in flight.
+//   * math is DMMA.8x8x4 (mma.sync.m8n8k4.f64): FP64 has no tcgen05 kind, DMMA is the FP64 tensor pipe.
+//   mma M <-> j, mma N <-> i, so each thread owns two consecutive rows i of a column j: double2 epilogue on the
+//   column-major output.
+#pragma once
+#include "common.cuh"
+
+namespace psoap {
+
+constexpr int BI = 128, BJ = 64, BK = 16, STAGES = 4;
+constexpr int SA = BI + 4, SB = BJ + 4;
+constexpr int STAGE_DOUBLES = BK * SA + BK * SB;
+constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8;
+constexpr int GEMM_WARPS = 8;
+constexpr uint32_t WARP_TX_BYTES = 2 * (BI * 8) + 2 * (BJ * 8);  // one warp's share of a stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+struct TileDesc {
+    const double* Ai;  // [128 rows, k] column-major, leading dimension lda
+    int64_t lda;
+    const double* Bj;  // [64 rows, k]
+    int64_t ldb;
+    int kbeg, KT;      // k range [kbeg, kbeg + 16 KT), KT >= 1
+    double* C;         // [128, 64] column-major output tile
+    int64_t ldc;
+};
+
+// trsm tiles: rows below panel kb.  tile t -> row tile I = kb+1 + t/2, column half jh = t%2:
+//   P[I*128 + :, jh*64 + :] = W[I*128 + :, kb*128 + (0 .. (jh+1)*64)] * Linv[jh*64 + :, same]^T
+struct TrsmSrc {
+    const double* W;
+    int64_t ld;
+    int kb, kbeg;
+    const double* Linv;
+    double* P;
+    int64_t ldp;
+    __device__ __forceinline__ TileDesc tile(int t) const {
+        const int I = kb + 1 + (t >> 1), jh = t & 1;
+        const int kend = (jh + 1) * BJ;
+        const int kb0 = min(kbeg, kend - BK);  // keep KT >= 1 (leading identity-padding columns only add zeros)
+        TileDesc d;
+        d.Ai = W + (int64_t)I * NB + (int64_t)kb * NB * ld;
+        d.lda = ld;
+        d.Bj = Linv + jh * BJ;
+        d.ldb = NB;
+        d.kbeg = kb0;
+        d.KT = (kend - kb0) / BK;
+        d.C = P + (int64_t)I * NB + (int64_t)jh * BJ * ldp;
+        d.ldc = ldp;
+        return d;
+    }
+};
+
+// syrk tiles: W[I, J] -= P_I P_J^T over the row tiles I = kb+1+r, r in [0, R).  Row r owns the 128 x 64 tiles
+// jrel in [0, 2r+2).  part 0: all of them; part 1: jrel < 2 (the next panel's block column); part 2: jrel >= 2.
+struct SyrkSrc {
+    double* W;
+    int64_t ld;
+    int kb, kbeg;
+    const double* P;
+    int64_t ldp;
+    int part;
+    __device__ __forceinline__ TileDesc tile(int t) const {
+        int r, jrel;
+        if (part == 1) {
+            r = t >> 1;
+            jrel = t & 1;
+        } else if (part == 0) {
+            r = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+            while ((r + 1) * (r + 2) <= t) ++r;
+            while (r * (r + 1) > t) --r;
+            jrel = t - r * (r + 1);
+        } else {
+            r = (int)((sqrt(4.0 * (double)t + 1.0) + 1.0) * 0.5);
+            while ((r + 1) * r <= t) ++r;
+            while (r * (r - 1) > t) --r;
+            jrel = 2 + t - r * (r - 1);
+        }
+        const int I = kb + 1 + r;
+        const int J64 = 2 * (kb + 1) + jrel;
+        TileDesc d;
+        d.Ai = P + (int64_t)I * NB;
+        d.lda = ldp;
+        d.Bj = P + (int64_t)J64 * BJ;
+        d.ldb = ldp;
+        d.kbeg = kbeg;
+        d.KT = (NB - kbeg) / BK;
+        d.C = W + (int64_t)I * NB + (int64_t)J64 * BJ * ld;
+        d.ldc = ld;
+        return d;
+    }
+};
+
+template <int MODE, class Src>  // MODE 0: C = acc, 1: C -= acc
+__device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride,
+                                                double* sm) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g4 = lane >> 2, tq = lane & 3;
+    const int wi = warp & 3, wj = warp >> 2;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * STAGE_DOUBLES);
+    uint64_t* empty = full + STAGES;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], GEMM_WARPS);
+            mbar_init(&empty[s], GEMM_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer cursor: which (tile, k-chunk) the next issued stage belongs to
+    int p_tile = first_tile, p_kt = 0, produced = 0;
+    bool p_valid = p_tile < ntiles;
+    TileDesc pd;
+    if (p_valid) pd = src.tile(p_tile);
+    auto produce = [&]() {
+        const int s = produced % STAGES;
+        if (lane == 0) {
+            if (produced >= STAGES) mbar_wait(&empty[s], ((produced / STAGES) - 1) & 1);
+            double* sA = sm + s * STAGE_DOUBLES;
+            double* sB = sA + BK * SA;
+            const int k0 = pd.kbeg + p_kt * BK;
+            mbar_arrive_expect_tx(&full[s], WARP_TX_BYTES);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = 2 * warp + cc;
+                tma_bulk_load(sA + c * SA, pd.Ai + (int64_t)(k0 + c) * pd.lda, BI * 8, &full[s]);
+                tma_bulk_load(sB + c * SB, pd.Bj + (int64_t)(k0 + c) * pd.ldb, BJ * 8, &full[s]);
+            }
+        }
+        ++produced;
+        if (++p_kt == pd.KT) {
+            p_kt = 0;
+            p_tile += tile_stride;
+            p_valid = p_tile < ntiles;
+            if (p_valid) pd = src.tile(p_tile);
+        }
+    };
+#pragma unroll 1
+    for (int s = 0; s < STAGES - 1 && p_valid; ++s) produce();
+
+    int g = 0;  // consumed items
+#pragma unroll 1
+    for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
+        const TileDesc td = src.tile(tile);
+        double* cbase = td.C + (wi * 32 + tq * 2) + (int64_t)(wj * 32 + g4) * td.ldc;
+        if (MODE == 1) {
+#pragma unroll
+            for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni += 2) prefetch_l2(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
+        }
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+#pragma unroll 1
+        for (int kt = 0; kt < td.KT; ++kt, ++g) {
+            if (p_valid) produce();  // refills the stage consumed one item ago
+            const int s = g % STAGES;
+            mbar_wait(&full[s], (g / STAGES) & 1);
+            const double* sA = sm + s * STAGE_DOUBLES;
+            const double* sB = sA + BK * SA;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mj = 0; mj < 4; ++mj) a[mj] = sB[(kk * 4 + tq) * SB + wj * 32 + mj * 8 + g4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = sA[(kk * 4 + tq) * SA + wi * 32 + ni * 8 + g4];
+#pragma unroll
+                for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
+            }
+            // Release the stage only after this warp's fragment loads have RETURNED: ptxas is free to hoist the
+            // arrive above the trailing DMMAs (it has no register dependence on them), and an mbarrier arrive
+            // is not ordered behind ld.shared still queued in the LSU.  fence.acq_rel.cta (MEMBAR.CTA) drains them.
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        if (MODE == 0) {
+#pragma unroll
+            for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) =
+                        make_double2(acc[mj][ni][0], acc[mj][ni][1]);
+        } else {
+#pragma unroll
+            for (int mj = 0; mj < 4; ++mj) {
+                double2 cv[4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    cv[ni] = *reinterpret_cast<const double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    cv[ni].x -= acc[mj][ni][0];
+                    cv[ni].y -= acc[mj][ni][1];
+                    *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) = cv[ni];
+                }
+            }
+        }
+    }
+}
+
+// Persistent launch geometry: `nctas` CTAs walk the tiles round-robin.
+__global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) {
+    extern __shared__ double sm[];
+    gemm_persistent<0>(src, ntiles, blockIdx.x, gridDim.x, sm);
+}
+
+// Blocks [0, nctas) are persistent tile workers; blocks [nctas, nctas + nres) update the residual
+// r_I -= P_I y_k for row tile I = kb+1 + (block - nctas) (deterministic two-half reduction).
+__global__ void __launch_bounds__(256, 2)
+syrk2_kernel(SyrkSrc src, int ntiles, int nctas, const double* __restrict__ yk, double* __restrict__ rvec) {
+    extern __shared__ double sm[];
+    if ((int)blockIdx.x < nctas) {
+        gemm_persistent<1>(src, ntiles, blockIdx.x, nctas, sm);
+    } else {
+        const int I = src.kb + 1 + ((int)blockIdx.x - nctas);
+        const int tid = threadIdx.x;
+        const int row = tid & (NB - 1), half = tid >> 7;
+        const double* p = src.P + (int64_t)I * NB + row + (int64_t)half * 64 * src.ldp;
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < 64; ++c) s = fma(p[(int64_t)c * src.ldp], yk[half * 64 + c], s);
+        sm[tid] = s;
+        __syncthreads();
+        if (half == 0) rvec[I * NB + row] -= (sm[row] + sm[NB + row]);
+    }
+}
+
+}  // namespace psoap
