@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
@@ -137,6 +137,10 @@ struct SyrkSrc {
     }
 };
 
+__device__ __forceinline__ double flip_sign(double x) {  // integer pipe, keeps the FP64 pipe for DMMA
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+
 template <int MODE, class Src>  // MODE 0: C = acc, 1: C -= acc
 __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride,
                                                 double* sm) {
@@ -156,7 +160,9 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     }
     __syncthreads();
 
-    // ---- producer cursor: which (tile, k-chunk) the next issued stage belongs to
+    // ---- producer cursor: which (tile, k-chunk) the next issued stage belongs to.  The stage consumed at
+    // item g is refilled at item g + 2 (LAG), so the producing lane practically never spins on the slowest warp.
+    constexpr int LAG = 2;
     int p_tile = first_tile, p_kt = 0, produced = 0;
     bool p_valid = p_tile < ntiles;
     TileDesc pd;
@@ -185,30 +191,65 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
         }
     };
 #pragma unroll 1
-    for (int s = 0; s < STAGES - 1 && p_valid; ++s) produce();
+    for (int s = 0; s < STAGES - LAG && p_valid; ++s) produce();
+
+    const int64_t coff0 = (wi * 32 + tq * 2);
+    const int joff0 = wj * 32 + g4;
+    if (MODE == 1 && first_tile < ntiles) {  // the first tile's C lines: towards L2 now
+        const TileDesc t0 = src.tile(first_tile);
+        const double* c0 = t0.C + coff0 + (int64_t)joff0 * t0.ldc;
+#pragma unroll
+        for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni += 2) prefetch_l2(c0 + ni * 8 + (int64_t)(mj * 8) * t0.ldc);
+    }
 
     int g = 0;  // consumed items
 #pragma unroll 1
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
         const TileDesc td = src.tile(tile);
-        double* cbase = td.C + (wi * 32 + tq * 2) + (int64_t)(wj * 32 + g4) * td.ldc;
+        double* cbase = td.C + coff0 + (int64_t)joff0 * td.ldc;
+        double acc[4][4][2];
         if (MODE == 1) {
+            // C is read straight into the accumulators at tile start (its lines were prefetched into L2 one tile
+            // ago); the DMMAs then run on -C so that the epilogue is a sign flip and a store, with no load latency.
 #pragma unroll
             for (int mj = 0; mj < 4; ++mj)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni += 2) prefetch_l2(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
+                    acc[mj][ni][0] = v.x;
+                    acc[mj][ni][1] = v.y;
+                }
+            if (tile + tile_stride < ntiles) {  // next tile's C lines: towards L2 while this tile computes
+                const TileDesc tn = src.tile(tile + tile_stride);
+                const double* cn = tn.C + coff0 + (int64_t)joff0 * tn.ldc;
+#pragma unroll
+                for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni += 2) prefetch_l2(cn + ni * 8 + (int64_t)(mj * 8) * tn.ldc);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         }
-        double acc[4][4][2];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
 #pragma unroll 1
         for (int kt = 0; kt < td.KT; ++kt, ++g) {
-            if (p_valid) produce();  // refills the stage consumed one item ago
+            if (p_valid) produce();  // refills the stage consumed LAG items ago
             const int s = g % STAGES;
             mbar_wait(&full[s], (g / STAGES) & 1);
+            if (MODE == 1 && kt == 0) {
+#pragma unroll
+                for (int mj = 0; mj < 4; ++mj)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        acc[mj][ni][0] = flip_sign(acc[mj][ni][0]);
+                        acc[mj][ni][1] = flip_sign(acc[mj][ni][1]);
+                    }
+            }
             const double* sA = sm + s * STAGE_DOUBLES;
             const double* sB = sA + BK * SA;
 #pragma unroll
@@ -231,28 +272,19 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
-        if (MODE == 0) {
 #pragma unroll
-            for (int mj = 0; mj < 4; ++mj)
+        for (int mj = 0; mj < 4; ++mj)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                    *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) =
-                        make_double2(acc[mj][ni][0], acc[mj][ni][1]);
-        } else {
-#pragma unroll
-            for (int mj = 0; mj < 4; ++mj) {
-                double2 cv[4];
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                    cv[ni] = *reinterpret_cast<const double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    cv[ni].x -= acc[mj][ni][0];
-                    cv[ni].y -= acc[mj][ni][1];
-                    *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) = cv[ni];
+            for (int ni = 0; ni < 4; ++ni) {
+                double2 v;
+                if (MODE == 1) {
+                    v.x = flip_sign(acc[mj][ni][0]);
+                    v.y = flip_sign(acc[mj][ni][1]);
+                } else {
+                    v = make_double2(acc[mj][ni][0], acc[mj][ni][1]);
                 }
+                *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) = v;
             }
-        }
     }
 }
 

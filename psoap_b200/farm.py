@@ -41,7 +41,7 @@ class ChunkFarm:
     rank/world_size: static partition of the chunks over GPUs; process_group: torch.distributed group (or None).
     """
 
-    def __init__(self, model, chunks, mu_GP=1.0, soften=1.0, nbranch=8, rank=0, world_size=1, process_group=None):
+    def __init__(self, model, chunks, mu_GP=1.0, soften=1.0, nbranch=32, rank=0, world_size=1, process_group=None):
         lib = _lib.load()
         torch = _lib.torch_cuda()
         self.model = model
