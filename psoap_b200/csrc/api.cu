@@ -49,7 +49,8 @@ inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
 std::once_flag g_attr_once;
 int g_attr_status = 0;
 int g_num_sms = 148;
-inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, 2 * g_num_sms)); }
+int g_ctas_per_sm = 2;
+inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
@@ -61,6 +62,7 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         g_attr_status = (int)e;
+        if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));

@@ -112,12 +112,12 @@ struct SyrkSrc {
             r = t >> 1;
             jrel = t & 1;
         } else if (part == 0) {
-            r = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+            r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // FP32: the FP64 pipe belongs to DMMA
             while ((r + 1) * (r + 2) <= t) ++r;
             while (r * (r + 1) > t) --r;
             jrel = t - r * (r + 1);
         } else {
-            r = (int)((sqrt(4.0 * (double)t + 1.0) + 1.0) * 0.5);
+            r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
             while ((r + 1) * r <= t) ++r;
             while (r * (r - 1) > t) --r;
             jrel = 2 + t - r * (r - 1);
