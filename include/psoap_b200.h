@@ -139,10 +139,10 @@ int psoap_farm_destroy(psoap_farm *farm);
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* Register-resident DMMA.8x8x4 loop on all SMs: measured FP64 tensor-pipe peak in TFLOP/s (synchronous). */
 int psoap_fp64_peak_tflops(double *tflops_out);
-/* Times the dominant kernel (the DMMA trailing update, csrc/chol.cuh syrk_kernel) alone: `reps` launches of the
- * rank-128 update of an m x m lower triangle, CUDA events on the launching stream.  flops_per_launch is the
- * algorithmic count 128 m (m + 128). Synchronous. */
-int psoap_bench_syrk(int64_t m, int reps, double *avg_ms_out, double *flops_per_launch_out);
+/* Times the dominant kernel (the DMMA trailing update, csrc/gemm.cuh syrk2_kernel) alone: `reps` launches of the
+ * rank-K update (K = 128 or 256) of an m x m lower triangle, CUDA events on the launching stream.
+ * flops_per_launch is the algorithmic count K m (m + 128). Synchronous. */
+int psoap_bench_syrk(int64_t m, int K, int reps, double *avg_ms_out, double *flops_per_launch_out);
 /* Number of kernels launched by this library since load (for bench.py's gpu_launches). */
 int64_t psoap_launch_count(void);
 

@@ -64,7 +64,7 @@ SIGNATURES = {
     "psoap_farm_launches_per_eval": (ctypes.c_int, [vp]),
     "psoap_farm_destroy": (ctypes.c_int, [vp]),
     "psoap_fp64_peak_tflops": (ctypes.c_int, [c_double_p]),
-    "psoap_bench_syrk": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p]),
+    "psoap_bench_syrk": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
     "psoap_launch_count": (ctypes.c_int64, []),
 }
 

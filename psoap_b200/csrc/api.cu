@@ -73,7 +73,7 @@ int set_kernel_attributes() {
 // L_kk^-1, residual, y, accumulators, info.
 struct FactorWs {
     double* W;
-    double* P[2];
+    double* P[2];   // two pair buffers, each column-major [Nt, 256] (two adjacent 128-wide panels)
     double* Linv;
     double* rvec;
     double* y;
@@ -85,7 +85,7 @@ struct FactorWs {
 size_t factor_ws_bytes(int64_t Nt) {
     size_t b = 0;
     b += align_up((size_t)Nt * Nt * 8, 256);
-    b += 2 * align_up((size_t)Nt * NB * 8, 256);
+    b += 2 * align_up((size_t)Nt * 2 * NB * 8, 256);
     b += align_up((size_t)NB * NB * 8, 256);
     b += 2 * align_up((size_t)Nt * 8, 256);
     b += align_up(8 * 8, 256);
@@ -98,8 +98,8 @@ void carve_factor_ws(char* base, int64_t Nt, FactorWs* ws, bool with_W) {
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
     ws->Nt = Nt;
     ws->W = with_W ? (double*)take((size_t)Nt * Nt * 8) : nullptr;
-    ws->P[0] = (double*)take((size_t)Nt * NB * 8);
-    ws->P[1] = (double*)take((size_t)Nt * NB * 8);
+    ws->P[0] = (double*)take((size_t)Nt * 2 * NB * 8);
+    ws->P[1] = (double*)take((size_t)Nt * 2 * NB * 8);
     ws->Linv = (double*)take((size_t)NB * NB * 8);
     ws->rvec = (double*)take((size_t)Nt * 8);
     ws->y = (double*)take((size_t)Nt * 8);
@@ -117,53 +117,81 @@ struct Lanes {
 
 // Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
 // (T_elim == T_total: plain Cholesky).  The trailing block is left holding the Schur complement.
+//
+// Panels are processed in PAIRS (a, b = a+1): after panel a is factored its update is applied to block column b
+// only (K = 128, 2R tiles); then b is factored and the trailing matrix gets ONE rank-256 update with [P_a | P_b],
+// which halves the read-modify-write traffic and the per-tile overhead of the dominant kernel.
+// Look-ahead: the rank-256 update first covers the next pair's two block columns (part 1); the next pair's
+// head (potrf, trsm, column update, potrf, trsm) then runs on the side stream under the rest of the update.
 int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
                   const int* sentinel, double* result) {
-    cudaStream_t st = ln.main;
+    const int64_t ldp = ws.Nt;
+    auto pbuf = [&](int q) { return ws.P[q & 1]; };
+    auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
     auto potrf = [&](cudaStream_t s, int kb) {
         potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
                                                      ws.info, sentinel, kb == T_elim - 1, result);
     };
-    auto trsm = [&](cudaStream_t s, int kb) {
+    auto trsm = [&](cudaStream_t s, int kb, int q, int col0) {
         const int R = T_total - kb - 1;
         TrsmSrc src;
         src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
-        src.Linv = ws.Linv; src.P = ws.P[kb & 1]; src.ldp = ws.Nt;
+        src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
         trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
     };
-    auto syrk = [&](cudaStream_t s, int kb, int part) {
-        const int R = T_total - kb - 1;
+    // update of row tiles [row0, T_total) with k range [kbeg, kend) of pair buffer q; residual with y of panel ykb
+    auto syrk = [&](cudaStream_t s, int q, int row0, int kend, int part, int ncol1, int ykb, int res_col0) {
+        const int R = T_total - row0;
         SyrkSrc src;
-        src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
-        src.P = ws.P[kb & 1]; src.ldp = ws.Nt; src.part = part;
-        const int ntiles = part == 0 ? R * (R + 1) : (part == 1 ? 2 * R : R * (R - 1));
+        src.W = W; src.ld = ld; src.row0 = row0; src.kbeg = kbeg_of(q); src.kend = kend;
+        src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = ncol1;
+        const int ntiles = syrk_ntiles(R, part, ncol1);
         const int nres = part == 2 ? 0 : R;
-        const int nctas = persistent_ctas(ntiles);
-        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, ws.y + (int64_t)kb * NB, ws.rvec);
+        if (ntiles + nres == 0) return;
+        const int nctas = ntiles > 0 ? persistent_ctas(ntiles) : 0;
+        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, ws.y + (int64_t)ykb * NB, ws.rvec, res_col0);
+        ++g_launches;
     };
-    potrf(st, 0);
-    LAUNCH_CHECK();
-    if (T_total > 1) { trsm(st, 0); LAUNCH_CHECK(); }
-    for (int kb = 0; kb < T_elim; ++kb) {
-        const int R = T_total - kb - 1;
-        if (R <= 0) break;
-        const bool next = kb + 1 < T_elim;
-        if (!next) { syrk(st, kb, 0); LAUNCH_CHECK(); break; }
-        if (ln.side == nullptr) {
-            syrk(st, kb, 0); LAUNCH_CHECK();
-            potrf(st, kb + 1); LAUNCH_CHECK();
-            if (R > 1) { trsm(st, kb + 1); LAUNCH_CHECK(); }
+    const int npairs = (T_elim + 1) / 2;
+    // everything of pair q that precedes its big update
+    auto head = [&](cudaStream_t s, int q) -> int {
+        const int a = 2 * q, b = a + 1;
+        potrf(s, a); LAUNCH_CHECK();
+        if (T_total - a - 1 <= 0) return PSOAP_OK;
+        trsm(s, a, q, 0); LAUNCH_CHECK();
+        if (b >= T_elim) return PSOAP_OK;
+        syrk(s, q, a + 1, NB, 1, 2, a, 0);          // block column b only (+ residual of panel a)
+        potrf(s, b); LAUNCH_CHECK();
+        if (T_total - b - 1 > 0) { trsm(s, b, q, NB); LAUNCH_CHECK(); }
+        return PSOAP_OK;
+    };
+    // the big update of pair q: rank 256 when the pair is complete, rank 128 for a trailing single panel
+    auto update = [&](cudaStream_t s, int q, int part, int ncol1) {
+        const int a = 2 * q, b = a + 1;
+        if (b < T_elim) syrk(s, q, b + 1, 2 * NB, part, ncol1, b, NB);
+        else syrk(s, q, a + 1, NB, part, ncol1, a, 0);
+    };
+    int rc = head(ln.main, 0);
+    if (rc) return rc;
+    for (int q = 0; q < npairs; ++q) {
+        const bool next = q + 1 < npairs;
+        if (!next || ln.side == nullptr) {
+            update(ln.main, q, 0, 2);
+            if (next) { rc = head(ln.main, q + 1); if (rc) return rc; }
             continue;
         }
-        syrk(st, kb, 1); LAUNCH_CHECK();
-        CUDA_TRY(cudaEventRecord(ln.e1, st));
+        const int ncol1 = (2 * (q + 1) + 1 < T_elim) ? 4 : 2;   // block columns the next pair's head touches
+        update(ln.main, q, 1, ncol1);
+        CUDA_TRY(cudaEventRecord(ln.e1, ln.main));
         CUDA_TRY(cudaStreamWaitEvent(ln.side, ln.e1, 0));
-        potrf(ln.side, kb + 1); LAUNCH_CHECK();
-        if (R > 1) { trsm(ln.side, kb + 1); LAUNCH_CHECK(); }
+        rc = head(ln.side, q + 1);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ln.e2, ln.side));
-        if (R > 1) { syrk(st, kb, 2); LAUNCH_CHECK(); }
-        CUDA_TRY(cudaStreamWaitEvent(st, ln.e2, 0));
+        update(ln.main, q, 2, ncol1);
+        CUDA_TRY(cudaStreamWaitEvent(ln.main, ln.e2, 0));
     }
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e_));
     return PSOAP_OK;
 }
 
@@ -623,22 +651,23 @@ int psoap_farm_destroy(psoap_farm* f) {
     return PSOAP_OK;
 }
 
-// Times the trailing-update kernel (syrk_kernel, the dominant kernel of the path) alone: `reps` launches of the
-// rank-128 update of an m x m lower triangle (m a multiple of 128), CUDA events on a private stream.
-// flops_per_launch is the algorithmic count 128 * m * (m + 128) (2 flops per multiply-add on the lower tiles).
-int psoap_bench_syrk(int64_t m, int reps, double* avg_ms_out, double* flops_per_launch_out) {
-    if (m < NB || m % NB || reps < 1 || !avg_ms_out) return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
+// Times the trailing-update kernel (syrk2_kernel, the dominant kernel of the path) alone: `reps` launches of the
+// rank-K update (K = 128 or 256) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
+// stream.  flops_per_launch is the algorithmic count K * m * (m + 128) (2 flops per multiply-add, lower tiles).
+int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
+    if (m < NB || m % NB || reps < 1 || !avg_ms_out || (K != NB && K != 2 * NB))
+        return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
     int rc = set_kernel_attributes();
     if (rc) return rc;
     double *W = nullptr, *P = nullptr, *y = nullptr, *r = nullptr;
     CUDA_TRY(cudaMalloc(&W, (size_t)m * m * 8));
-    CUDA_TRY(cudaMalloc(&P, (size_t)m * NB * 8));
+    CUDA_TRY(cudaMalloc(&P, (size_t)m * 2 * NB * 8));
     CUDA_TRY(cudaMalloc(&y, NB * 8));
     CUDA_TRY(cudaMalloc(&r, (size_t)m * 8));
     CUDA_TRY(cudaMemset(W, 0, (size_t)m * m * 8));
     CUDA_TRY(cudaMemset(y, 0, NB * 8));
     CUDA_TRY(cudaMemset(r, 0, (size_t)m * 8));
-    std::vector<double> hp((size_t)m * NB);
+    std::vector<double> hp((size_t)m * 2 * NB);
     for (size_t i = 0; i < hp.size(); ++i) hp[i] = 1e-3 * (double)((i * 2654435761u) % 1000) - 0.5;
     CUDA_TRY(cudaMemcpy(P, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice));
     cudaStream_t st;
@@ -648,11 +677,11 @@ int psoap_bench_syrk(int64_t m, int reps, double* avg_ms_out, double* flops_per_
     CUDA_TRY(cudaEventCreate(&e1));
     const int R = (int)(m / NB), ntiles = R * (R + 1);
     SyrkSrc src;
-    src.W = W; src.ld = m; src.kb = -1; src.kbeg = 0; src.P = P; src.ldp = m; src.part = 0;
+    src.W = W; src.ld = m; src.row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
     const int nctas = persistent_ctas(ntiles);
-    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r); ++g_launches; }
+    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r, 0); ++g_launches; }
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r); ++g_launches; }
+    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r, 0); ++g_launches; }
     cudaEventRecord(e1, st);
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -660,7 +689,7 @@ int psoap_bench_syrk(int64_t m, int reps, double* avg_ms_out, double* flops_per_
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     cudaFree(W); cudaFree(P); cudaFree(y); cudaFree(r);
     *avg_ms_out = ms / reps;
-    if (flops_per_launch_out) *flops_per_launch_out = 128.0 * (double)m * (double)(m + NB);
+    if (flops_per_launch_out) *flops_per_launch_out = (double)K * (double)m * (double)(m + NB);
     return PSOAP_OK;
 }
 

@@ -97,45 +97,66 @@ struct TrsmSrc {
     }
 };
 
-// syrk tiles: W[I, J] -= P_I P_J^T over the row tiles I = kb+1+r, r in [0, R).  Row r owns the 128 x 64 tiles
-// jrel in [0, 2r+2).  part 0: all of them; part 1: jrel < 2 (the next panel's block column); part 2: jrel >= 2.
+// syrk tiles: W[I, J] -= P_I P_J^T over the row tiles I = row0 + r, r in [0, R), with P the panel buffer
+// [Nt, 256] (two adjacent 128-wide panels; k range [kbeg, kend), kend = 128 or 256).  Row r owns the 128 x 64
+// tiles jrel in [0, 2r+2), J64 = 2 row0 + jrel.
+//   part 0: all of them
+//   part 1: jrel < ncol1 (ncol1 = 2 or 4: the next one or two panels' block columns, for look-ahead)
+//   part 2: jrel >= ncol1
 struct SyrkSrc {
     double* W;
     int64_t ld;
-    int kb, kbeg;
+    int row0, kbeg, kend;
     const double* P;
     int64_t ldp;
-    int part;
+    int part, ncol1;
     __device__ __forceinline__ TileDesc tile(int t) const {
         int r, jrel;
-        if (part == 1) {
-            r = t >> 1;
-            jrel = t & 1;
-        } else if (part == 0) {
+        if (part == 0) {
             r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // FP32: the FP64 pipe belongs to DMMA
             while ((r + 1) * (r + 2) <= t) ++r;
             while (r * (r + 1) > t) --r;
             jrel = t - r * (r + 1);
+        } else if (part == 1) {
+            if (ncol1 == 2) {
+                r = t >> 1;
+                jrel = t & 1;
+            } else if (t < 2) {
+                r = 0;
+                jrel = t;
+            } else {
+                r = 1 + ((t - 2) >> 2);
+                jrel = (t - 2) & 3;
+            }
         } else {
-            r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
-            while ((r + 1) * r <= t) ++r;
-            while (r * (r - 1) > t) --r;
-            jrel = 2 + t - r * (r - 1);
+            int v = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
+            while ((v + 1) * v <= t) ++v;
+            while (v * (v - 1) > t) --v;
+            jrel = ncol1 + t - v * (v - 1);
+            r = v + (ncol1 >> 1) - 1;
         }
-        const int I = kb + 1 + r;
-        const int J64 = 2 * (kb + 1) + jrel;
+        const int I = row0 + r;
+        const int J64 = 2 * row0 + jrel;
         TileDesc d;
         d.Ai = P + (int64_t)I * NB;
         d.lda = ldp;
         d.Bj = P + (int64_t)J64 * BJ;
         d.ldb = ldp;
         d.kbeg = kbeg;
-        d.KT = (NB - kbeg) / BK;
+        d.KT = (kend - kbeg) / BK;
         d.C = W + (int64_t)I * NB + (int64_t)J64 * BJ * ld;
         d.ldc = ld;
         return d;
     }
 };
+
+// number of tiles of a syrk launch over R row tiles
+__host__ __device__ inline int syrk_ntiles(int R, int part, int ncol1) {
+    const int h = ncol1 >> 1;
+    if (part == 0) return R * (R + 1);
+    if (part == 1) return ncol1 == 2 ? 2 * R : (R >= 1 ? 2 + 4 * (R - 1) : 0);
+    return R > h ? (R - h) * (R - h + 1) : 0;
+}
 
 __device__ __forceinline__ double flip_sign(double x) {  // integer pipe, keeps the FP64 pipe for DMMA
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
@@ -295,17 +316,18 @@ __global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) 
 }
 
 // Blocks [0, nctas) are persistent tile workers; blocks [nctas, nctas + nres) update the residual
-// r_I -= P_I y_k for row tile I = kb+1 + (block - nctas) (deterministic two-half reduction).
+// r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + (block - nctas) (deterministic two-half sum).
 __global__ void __launch_bounds__(256, 2)
-syrk2_kernel(SyrkSrc src, int ntiles, int nctas, const double* __restrict__ yk, double* __restrict__ rvec) {
+syrk2_kernel(SyrkSrc src, int ntiles, int nctas, const double* __restrict__ yk, double* __restrict__ rvec,
+             int res_col0) {
     extern __shared__ double sm[];
     if ((int)blockIdx.x < nctas) {
         gemm_persistent<1>(src, ntiles, blockIdx.x, nctas, sm);
     } else {
-        const int I = src.kb + 1 + ((int)blockIdx.x - nctas);
+        const int I = src.row0 + ((int)blockIdx.x - nctas);
         const int tid = threadIdx.x;
         const int row = tid & (NB - 1), half = tid >> 7;
-        const double* p = src.P + (int64_t)I * NB + row + (int64_t)half * 64 * src.ldp;
+        const double* p = src.P + (int64_t)I * NB + row + (int64_t)(res_col0 + half * 64) * src.ldp;
         double s = 0.0;
 #pragma unroll 8
         for (int c = 0; c < 64; ++c) s = fma(p[(int64_t)c * src.ldp], yk[half * 64 + c], s);

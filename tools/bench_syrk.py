@@ -8,7 +8,8 @@ from psoap_b200 import _lib  # noqa: E402
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 lib = _lib.load()
 ms, fl = ctypes.c_double(), ctypes.c_double()
-_lib.check(lib.psoap_bench_syrk(m, reps, ctypes.byref(ms), ctypes.byref(fl)))
-print("m=%d avg_ms=%.4f tflops=%.2f" % (m, ms.value, fl.value / ms.value * 1e-9))
+_lib.check(lib.psoap_bench_syrk(m, K, reps, ctypes.byref(ms), ctypes.byref(fl)))
+print("m=%d K=%d avg_ms=%.4f tflops=%.2f" % (m, K, ms.value, fl.value / ms.value * 1e-9))
