@@ -50,6 +50,7 @@ std::once_flag g_attr_once;
 int g_attr_status = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
+int g_yield_lookahead = 1;
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
@@ -63,6 +64,7 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         g_attr_status = (int)e;
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
+        if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -148,7 +150,10 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         const int ntiles = syrk_ntiles(R, part, ncol1);
         const int nres = part == 2 ? 0 : R;
         if (ntiles + nres == 0) return;
-        const int nctas = ntiles > 0 ? persistent_ctas(ntiles) : 0;
+        // Under look-ahead the bulk update (part 2) gives up persistence: one tile per CTA, so SM slots free up
+        // continuously and the high-priority side stream (next pair's potrf/trsm) is scheduled into them.
+        const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
+        const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
         syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, ws.y + (int64_t)ykb * NB, ws.rvec, res_col0);
         ++g_launches;
     };
@@ -594,7 +599,7 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
     for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
     rc = PSOAP_OK;
     const char* la_env = getenv("PSOAP_FARM_LOOKAHEAD");
-    const bool lookahead = la_env ? (atoi(la_env) != 0) : true;
+    const bool lookahead = la_env ? (atoi(la_env) != 0) : (nbranch < 8);
     for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
         cudaStream_t sb = f->streams[b];
         cudaStreamWaitEvent(sb, f->events[nbranch], 0);

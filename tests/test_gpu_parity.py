@@ -296,3 +296,47 @@ def test_block_additivity(oracle, torch_cuda):
     joint = covariance.lnlike_f_g(None, lw[0], lw[1], np.concatenate([a["fl"], b["fl"]]),
                                   np.concatenate([a["sigma"], b["sigma"]]), *p[7:])
     assert rel_close(joint, parts[0] + parts[1], LNLIKE_RTOL)
+
+
+def test_repeatable_bits(oracle, torch_cuda):
+    """The same evaluation repeated gives the same bits (the TMA/mbarrier pipeline once raced here),
+    with and without an intervening synchronisation, and through the farm graph."""
+    from psoap_b200 import covariance, synthetic
+    from psoap_b200.farm import ChunkFarm
+    ch = synthetic.make_chunk("SB2", 20, 300, seed=1)  # N = 6000: several tiles per persistent CTA
+    p = synthetic.default_params("SB2")
+    vel = synthetic.host_velocities("SB2", p[:7], ch["date1D"])
+    t = torch_cuda
+    lw = [t.from_numpy(ch["lwl"] - vel[c][ch["epoch"]] / synthetic.c_kms).cuda() for c in range(2)]
+    fl, sg = t.from_numpy(ch["fl"]).cuda(), t.from_numpy(ch["sigma"]).cuda()
+    vals = {covariance.lnlike_f_g(None, lw[0], lw[1], fl, sg, *p[7:]) for _ in range(6)}
+    assert len(vals) == 1, vals
+    farm = ChunkFarm("SB2", [ch, synthetic.make_chunk("SB2", 20, 150, seed=2)])
+    fv = {farm.lnprob(p) for _ in range(4)}
+    assert len(fv) == 1, fv
+    farm.close()
+
+
+def test_c5_large_single_chunk(torch_cuda):
+    """BASELINE config C5 (N = 32768, 8.6 GB matrix) through size-independent properties: the data are laid out as
+    two far-apart halves (exactly zero cross-covariance), so the joint log-likelihood must equal the sum of the
+    halves, each of which is small enough to be cross-checked against cuSOLVER."""
+    from psoap_b200 import covariance, synthetic
+    p = synthetic.default_params("SB2")
+    halves, lws = [], []
+    for k, wl0 in enumerate((5000.0, 5600.0)):
+        ch = synthetic.make_chunk("SB2", 32, 512, seed=50 + k, wl0=wl0)  # 16384 pixels each
+        vel = synthetic.host_velocities("SB2", p[:7], ch["date1D"])
+        lw = np.stack([ch["lwl"] - vel[c][ch["epoch"]] / synthetic.c_kms for c in range(2)])
+        halves.append((ch, lw))
+        lws.append(lw)
+    parts = [covariance.lnlike_f_g(None, lw[0], lw[1], ch["fl"], ch["sigma"], *p[7:]) for ch, lw in halves]
+    ref0 = _torch_reference_lnlike(torch_cuda, list(halves[0][1]), halves[0][0]["fl"], halves[0][0]["sigma"], p[7:])
+    assert rel_close(parts[0], ref0, LNLIKE_RTOL), (parts[0], ref0)
+    lw = np.concatenate(lws, axis=1)
+    fl = np.concatenate([h[0]["fl"] for h in halves])
+    sg = np.concatenate([h[0]["sigma"] for h in halves])
+    assert lw.shape[1] == 32768
+    torch_cuda.cuda.empty_cache()
+    joint = covariance.lnlike_f_g(None, lw[0], lw[1], fl, sg, *p[7:])
+    assert np.isfinite(joint) and rel_close(joint, parts[0] + parts[1], LNLIKE_RTOL), (joint, parts)
