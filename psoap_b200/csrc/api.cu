@@ -51,10 +51,12 @@ int g_attr_status = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
+int g_potrf_version = 2;
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -65,6 +67,7 @@ int set_kernel_attributes() {
         g_attr_status = (int)e;
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
+        if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = atoi(c);
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -131,8 +134,12 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
     auto potrf = [&](cudaStream_t s, int kb) {
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
-                                                     ws.info, sentinel, kb == T_elim - 1, result);
+        if (g_potrf_version == 1)
+            potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
+                                                         ws.info, sentinel, kb == T_elim - 1, result);
+        else
+            potrf_diag2_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
+                                                          ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
     };
     auto trsm = [&](cudaStream_t s, int kb, int q, int col0) {
         const int R = T_total - kb - 1;

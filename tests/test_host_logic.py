@@ -86,3 +86,40 @@ def test_two_rank_gloo_reduction_equals_serial_sum(tmp_path, inf_case):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_param_registry_round_trip():
+    from psoap_b200 import utils
+    pars = dict(q=0.2, K=5.0, e=0.2, omega=10.0, P=10.0, T0=0.0, gamma=5.0, amp_f=0.1, l_f=5.0, amp_g=0.05, l_g=7.0)
+    fix = ["gamma", "T0"]
+    p = utils.convert_dict("SB2", fix, **pars)
+    assert len(p) == 9 and p[0] == 0.2 and p[-1] == 7.0
+    p_orb, p_GP = utils.convert_vector(p, "SB2", fix, **pars)
+    assert list(p_orb) == [0.2, 5.0, 0.2, 10.0, 10.0, 0.0, 5.0] and list(p_GP) == [0.1, 5.0, 0.05, 7.0]
+    assert utils.n_params_orb == {"SB1": 6, "SB2": 7, "ST1": 11, "ST2": 12, "ST3": 13}
+
+
+def test_priors_match_reference_bounds():
+    from psoap_b200 import sample
+    ok = ([0.2, 5.0, 0.2, 10.0, 10.0, 0.0, 5.0], [0.1, 5.0, 0.05, 7.0])
+    assert sample.prior_SB2(*ok) == 0.0
+    for idx, val in [(0, -0.1), (1, -1.0), (2, 1.5), (3, 451.0), (3, -91.0), (4, -1.0)]:
+        po = list(ok[0]); po[idx] = val
+        assert sample.prior_SB2(po, ok[1]) == -np.inf
+    assert sample.prior_SB2(ok[0], [0.1, -5.0, 0.05, 7.0]) == -np.inf
+    assert sample.prior_SB1([5.0, 0.2, 10.0, 10.0, 0.0, 5.0], [0.1, 5.0]) == 0.0
+
+
+def test_mh_sampler_recovers_a_gaussian():
+    from psoap_b200.sample import MHSampler
+    mean, sig = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    lnp = lambda p: float(-0.5 * np.sum(((p - mean) / sig) ** 2))
+    s = MHSampler(np.diag((1.2 * sig) ** 2), 2, lnp, seed=3)
+    s.run_mcmc(mean, 20000)
+    assert 0.2 < s.acceptance_fraction < 0.6
+    assert np.allclose(s.flatchain[2000:].mean(axis=0), mean, atol=0.1)
+    assert np.allclose(s.flatchain[2000:].std(axis=0), sig, rtol=0.1)
+    assert s.lnprobability.shape == (20000,)
+    s2 = MHSampler(np.diag((1.2 * sig) ** 2), 2, lnp, seed=3)
+    s2.run_mcmc(mean, 100)
+    assert np.array_equal(s2.flatchain, s.flatchain[:100])  # same seed, same chain: the replicated-rank contract
