@@ -340,3 +340,25 @@ def test_c5_large_single_chunk(torch_cuda):
     torch_cuda.cuda.empty_cache()
     joint = covariance.lnlike_f_g(None, lw[0], lw[1], fl, sg, *p[7:])
     assert np.isfinite(joint) and rel_close(joint, parts[0] + parts[1], LNLIKE_RTOL), (joint, parts)
+
+
+def test_sampler_chain_matches_oracle_at_visited_points(oracle, torch_cuda, tmp_path):
+    """psoap_b200.sample.run (the psoap-sample-parallel replacement): every stored lnprob is the oracle's farm
+    log-likelihood at the stored chain position; outputs are written like sample_parallel.py:442-443."""
+    from psoap_b200 import sample, synthetic, utils
+    chunks = [synthetic.make_chunk("SB2", 5, 40 + 9 * i, seed=700 + i, mask_frac=0.02 * i) for i in range(3)]
+    names = utils.registered_params["SB2"]
+    pars = dict(zip(names, synthetic.default_params("SB2")))
+    jumps = dict(q=0.002, K=0.02, e=0.002, omega=0.05, P=0.001, T0=0.001, gamma=0.01, amp_f=0.002, l_f=0.05,
+                 amp_g=0.002, l_g=0.05)
+    config = dict(model="SB2", parameters=pars, jumps=jumps, fix_params=["gamma"], samples=12, soften=1.0,
+                  outdir=str(tmp_path), opt_jump="does-not-exist.npy")
+    s = sample.run(config, chunks, run_index=3, seed=5, verbose=False)
+    assert s.flatchain.shape == (12, 10) and s.lnprobability.shape == (12,)
+    assert np.array_equal(np.load(tmp_path / "run03" / "flatchain.npy"), s.flatchain)
+    assert np.array_equal(np.load(tmp_path / "run03" / "lnprob.npy"), s.lnprobability)
+    for i in (0, 5, 11):
+        p_orb, p_GP = utils.convert_vector(s.flatchain[i], "SB2", ["gamma"], **pars)
+        ref, _ = oracle.farm_lnprob("SB2", np.concatenate([p_orb, p_GP]), chunks)
+        assert rel_close(s.lnprobability[i], ref, LNLIKE_RTOL), (i, s.lnprobability[i], ref)
+    assert s.naccepted >= 1
