@@ -167,6 +167,68 @@ potrf_diag_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, dou
     }
 }
 
+// Common tail of the diagonal-block kernels: logdet and pivot check, y_k = X r_k and its norm, L_kk^-1 to
+// global memory, Kahan accumulation across panels, and the final result record on the last panel.
+__device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const double* Xs, const double* dval,
+                                               const double* rs, double* red, double* __restrict__ Linv,
+                                               double* __restrict__ yk, double* __restrict__ acc,
+                                               int* __restrict__ info, const int* __restrict__ sentinel, int is_last,
+                                               double* __restrict__ result) {
+    // logdet contribution and pivot check
+    double lg = 0.0;
+    int bad = 0x7fffffff;
+    if (tid < NB) {
+        const double d = dval[tid];
+        lg = log(d);  // = 2 log L_jj (covariance.py:329)
+        if (!(d > 0.0)) bad = tid;
+    }
+    red[tid] = lg;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    const double lgsum = red[0];
+    __syncthreads();
+    double y = 0.0;
+    if (tid < NB) {
+        for (int c = 0; c <= tid; ++c) y = fma(Xs[c * XS + tid], rs[c], y);
+        yk[tid] = y;
+    }
+    red[tid] = y * y;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    const double qsum = red[0];
+    __syncthreads();
+    int* redi = reinterpret_cast<int*>(red);
+    redi[tid] = bad;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) redi[tid] = min(redi[tid], redi[tid + s]);
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e & (NB - 1), c = e >> 7;
+        Linv[e] = Xs[c * XS + r];
+    }
+    if (tid == 0) {
+        if (redi[0] != 0x7fffffff && info[0] == 0) info[0] = kb * NB + redi[0] - pad + 1;
+        kahan_add(&acc[0], &acc[1], lgsum);
+        kahan_add(&acc[2], &acc[3], qsum);
+        if (is_last) {
+            const int inf = info[0];
+            const bool flagged = (inf != 0) || (sentinel != nullptr && sentinel[0] != 0);
+            result[0] = flagged ? -CUDART_INF : -0.5 * (acc[2] + acc[0]);  // covariance.py:331
+            result[1] = acc[0];
+            result[2] = acc[2];
+            result[3] = (double)inf;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // potrf_diag2: same algorithm and register layout as potrf_diag, restructured so the 128 dependent pivots see
 // a short chain.  Within step j every thread first computes only the entries the NEXT step publishes (column
@@ -290,59 +352,119 @@ potrf_diag2_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     potrf2_block_steps<6>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
     potrf2_block_steps<7>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
     __syncthreads();
-    // logdet contribution and pivot check
-    double lg = 0.0;
-    int bad = 0x7fffffff;
-    if (tid < NB) {
-        const double d = dval[tid];
-        lg = log(d);  // = 2 log L_jj (covariance.py:329)
-        if (!(d > 0.0)) bad = tid;
-    }
-    red[tid] = lg;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    const double lgsum = red[0];
-    __syncthreads();
-    double y = 0.0;
-    if (tid < NB) {
-        for (int c = 0; c <= tid; ++c) y = fma(Xs[c * XS + tid], rs[c], y);
-        yk[tid] = y;
-    }
-    red[tid] = y * y;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    const double qsum = red[0];
-    __syncthreads();
-    int* redi = reinterpret_cast<int*>(red);
-    redi[tid] = bad;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) redi[tid] = min(redi[tid], redi[tid + s]);
-        __syncthreads();
-    }
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e & (NB - 1), c = e >> 7;
-        Linv[e] = Xs[c * XS + r];
-    }
-    if (tid == 0) {
-        if (redi[0] != 0x7fffffff && info[0] == 0) info[0] = kb * NB + redi[0] - pad + 1;
-        kahan_add(&acc[0], &acc[1], lgsum);
-        kahan_add(&acc[2], &acc[3], qsum);
-        if (is_last) {
-            const int inf = info[0];
-            const bool flagged = (inf != 0) || (sentinel != nullptr && sentinel[0] != 0);
-            result[0] = flagged ? -CUDART_INF : -0.5 * (acc[2] + acc[0]);  // covariance.py:331
-            result[1] = acc[0];
-            result[2] = acc[2];
-            result[3] = (double)inf;
+    potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// potrf_diag3: same algorithm and register layout again, with the per-step instruction count cut to the bone
+// (the step is issue bound: 8 warps x ~130 instructions on one SM).  The owners of column j scale it BEFORE
+// publishing (the pivot travels to them by warp shuffle, they sit in one half-warp), rows that are already
+// finished are published as zeros, so a consumer's step is 16 shared loads, <= 36 DFMA and a handful of
+// multiplies for the inverse part; no thread but the 16 column owners evaluates the reciprocal square root.
+// ------------------------------------------------------------------------------------------------------
+#ifdef PSOAP_POTRF_TRACE
+__device__ long long g_potrf_trace[8][128][5];   // [warp][step][phase] clock64 stamps (lab builds only)
+#define PSOAP_TRACE(ph) do { if ((tid & 31) == 0) g_potrf_trace[tid >> 5][j][ph] = clock64(); } while (0)
+#else
+#define PSOAP_TRACE(ph) do { } while (0)
+#endif
+
+template <int JQ>
+__device__ __forceinline__ void potrf3_block_steps(double (&M)[8][8], int ti, int tc, int tid, double* Xs, double* colb,
+                                                   double* rowb, double* scal, double* dval) {
+#pragma unroll 1
+    for (int jr = 0; jr < 16; ++jr) {
+        const int j = 16 * JQ + jr;
+        double* cb = colb + (j & 1) * NB;
+        double* rb = rowb + (j & 1) * NB;
+        PSOAP_TRACE(0);
+        // ---- publish: scaled column j (zeros for the finished rows), raw row j of the inverse part, pivot
+        if (tc == jr) {
+            const unsigned hmask = 0xFFFFu << (16 * (tid >> 4 & 1));
+            const double d = __shfl_sync(hmask, M[JQ][JQ], (tid & 16) + jr);
+            const double inv = rsqrt(d);
+#pragma unroll
+            for (int p = JQ; p < 8; ++p) {
+                const bool below = (p > JQ) || (ti > jr);
+                cb[ti + 16 * p] = below ? M[p][JQ] * inv : 0.0;
+            }
+            if (ti == jr) { scal[(j & 1) * 2] = d; scal[(j & 1) * 2 + 1] = inv; dval[j] = d; }
         }
+        if (ti == jr) {
+#pragma unroll
+            for (int q = 0; q <= JQ; ++q) rb[tc + 16 * q] = M[JQ][q];
+        }
+        PSOAP_TRACE(1);
+        __syncthreads();
+        PSOAP_TRACE(2);
+        // ---- consume
+        const double inv = scal[(j & 1) * 2 + 1];
+        if (tid < NB) {  // row j of X = L^-1 is final
+            const int c = tid;
+            Xs[c * XS + j] = (c < j) ? rb[c] * inv : ((c == j) ? inv : 0.0);
+        }
+        double li[8], w[8];
+#pragma unroll
+        for (int p = JQ; p < 8; ++p) li[p] = cb[ti + 16 * p];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int c = tc + 16 * q;
+            if (q > JQ) w[q] = cb[c];
+            else if (q < JQ) w[q] = rb[c] * inv;
+            else w[q] = (tc > jr) ? cb[c] : ((tc < jr) ? rb[c] * inv : inv);
+        }
+        const bool special = (tc == jr);
+        PSOAP_TRACE(3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int p = (q > JQ ? q : JQ); p < 8; ++p) {
+                const double base = (special && q == JQ) ? 0.0 : M[p][q];
+                M[p][q] = fma(-li[p], w[q], base);
+            }
+        }
+        PSOAP_TRACE(4);
     }
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, double* __restrict__ Linv,
+                   double* __restrict__ rvec, double* __restrict__ yk, double* __restrict__ acc,
+                   int* __restrict__ info, const int* __restrict__ sentinel, int is_last,
+                   double* __restrict__ result) {
+    extern __shared__ double sm[];
+    double* Xs = sm;                  // Xs[c*XS + r] = X[r][c], X = L^-1
+    double* colb = Xs + NB * XS;      // [2][NB]
+    double* rowb = colb + 2 * NB;     // [2][NB]
+    double* dval = rowb + 2 * NB;     // [NB] pivots d_j
+    double* rs = dval + NB;           // [NB] residual segment
+    double* red = rs + NB;            // [256]
+    double* scal = red + 256;         // [2][2]: pivot d_j and d_j^-1/2
+    const int tid = threadIdx.x;
+    const int ti = tid & 15, tc = tid >> 4;
+    const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
+
+    double M[8][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            if (p < q) { M[p][q] = 0.0; continue; }
+            const int i = ti + 16 * p, c = tc + 16 * q;
+            M[p][q] = (i >= c) ? A[i + (int64_t)c * ld] : 0.0;
+        }
+    if (tid < NB) rs[tid] = rvec[kb * NB + tid];
+
+    potrf3_block_steps<0>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<1>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<2>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<3>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<4>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<5>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<6>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    potrf3_block_steps<7>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
+    __syncthreads();
+    potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
 }
 
 // Register-resident DMMA loop: the FP64 tensor-pipe peak used as the roofline denominator.
