@@ -435,3 +435,53 @@ def farm_lnprob(model, p_full, chunks, use_ref_fill=False):
     for i, ch in enumerate(chunks):
         lnps[i] = chunk_lnprob(model, p_full, ch, use_ref_fill=use_ref_fill)
     return np.sum(lnps), lnps
+
+
+# --------------------------------------------------------------------------------------------------
+# Calibration — psoap/covariance.py:560-711
+# --------------------------------------------------------------------------------------------------
+def _cheb_design(x0, x1, x, fl_cal, order):
+    """covariance.py:584-595 / :669-680."""
+    from numpy.polynomial import Chebyshev as Ch
+    T = []
+    for i in range(0, order + 1):
+        coeff = [0 for j in range(i)] + [1]
+        T += [Ch(coeff, domain=[x0, x1])(x)]
+    T = np.array(T)
+    return fl_cal[:, np.newaxis] * T.T
+
+
+def _calibration_solve(A, B, C, D, fl_fixed, mu_GP):
+    """covariance.py:598-624 (identical body at :686-711)."""
+    B_cho = cho_factor(B)
+    fl_prime = mu_GP + np.dot(C, cho_solve(B_cho, (fl_fixed.flatten() - mu_GP)))
+    C_prime = A - np.dot(C, cho_solve(B_cho, C.T))
+    CP_cho = cho_factor(C_prime)
+    left = np.dot(D.T, cho_solve(CP_cho, D))
+    right = np.dot(D.T, cho_solve(CP_cho, fl_prime))
+    X = cho_solve(cho_factor(left), right)
+    return np.dot(D, X), X
+
+
+def optimize_calibration(lwl0, lwl1, lwl_cal, fl_cal, fl_fixed, A, B, C, order=1, mu_GP=1.0):
+    """covariance.py:560-624."""
+    return _calibration_solve(A, B, C, _cheb_design(lwl0, lwl1, lwl_cal, fl_cal, order), fl_fixed, mu_GP)
+
+
+def optimize_calibration_static(wl0, wl1, wl_cal, fl_cal, sigma_cal, wl_fixed, fl_fixed, sigma_fixed, amp, l_f, order=1,
+                                mu_GP=1.0):
+    """covariance.py:627-711."""
+    A, B = _K11(wl_cal, amp, l_f), _K11(wl_fixed, amp, l_f)
+    C = _K12(wl_cal, wl_fixed, amp, l_f)
+    A[np.diag_indices_from(A)] += sigma_cal ** 2
+    B[np.diag_indices_from(B)] += sigma_fixed ** 2
+    return _calibration_solve(A, B, C, _cheb_design(wl0, wl1, wl_cal, fl_cal, order), fl_fixed, mu_GP)
+
+
+def optimize_GP_f(wl_known, fl_known, sigma_known, amp_f, l_f, mu_GP=1.0):
+    """covariance.py:408-424."""
+    from scipy.optimize import minimize
+    N = len(wl_known)
+    V11 = np.empty((N, N), dtype=np.float64)
+    func = lambda x: -lnlike_f(V11, wl_known, fl_known, sigma_known, x[0], x[1], mu_GP)
+    return minimize(func, np.array([amp_f, l_f]), method="Nelder-Mead")["x"]

@@ -262,3 +262,103 @@ def predict_f(lwl_known, fl_known, sigma_known, lwl_predict, amp_f, l_f, mu_GP=1
     matrix_functions.fill_V12_sum(B.cross_block(0, lp.numel()), [lw], [lp], [amp_f], [l_f])
     Sigma, delta = B.schur(fl_d - float(mu_GP))
     return _out(mu_GP + delta, on_dev), _out(Sigma, on_dev)
+
+
+# --------------------------------------------------------------------------------------------------
+# Callers of the hot path that live in psoap.covariance: GP hyper-parameter fit and flux calibration
+# (covariance.py:408-424, :560-732).  Host logic as in the reference (scipy Nelder-Mead, numpy Chebyshev);
+# every O(N^3) piece goes through the same device kernels (lnlike_f, Schur complements).
+# --------------------------------------------------------------------------------------------------
+def optimize_GP_f(wl_known, fl_known, sigma_known, amp_f, l_f, mu_GP=1.0):
+    """covariance.py:408-424: Nelder-Mead on -lnlike_f, starting from (amp_f, l_f)."""
+    from scipy.optimize import minimize
+    lw, fl, sg = _lib.dev_f64(wl_known), _lib.dev_f64(fl_known), _lib.dev_f64(sigma_known)  # uploaded once
+
+    def func(x):
+        a, l = x
+        return -lnlike_f(None, lw, fl, sg, a, l, mu_GP)
+
+    return minimize(func, np.array([amp_f, l_f]), method="Nelder-Mead")["x"]
+
+
+def _chebyshev_design(x0, x1, x, fl_cal, order):
+    """D = fl_cal[:, None] * T^T with T_k the Chebyshev polynomials on [x0, x1] (covariance.py:584-593)."""
+    from numpy.polynomial import Chebyshev as Ch
+    x = np.asarray(x, dtype=np.float64)
+    T = np.array([Ch([0] * k + [1], domain=[x0, x1])(x) for k in range(order + 1)])
+    return np.asarray(fl_cal, dtype=np.float64)[:, np.newaxis] * T.T
+
+
+def _calibrate(fill_blocks, n_cal, n_fixed, resid_fixed, D, mu_GP):
+    """Common core of optimize_calibration / optimize_calibration_static (covariance.py:598-624, :686-711):
+    fl' = mu + C B^-1 (fl_fixed - mu), C' = A - C B^-1 C^T (first Schur complement); then the least squares
+    X = (D^T C'^-1 D)^-1 D^T C'^-1 fl' through a second Schur complement with border D^T."""
+    from scipy.linalg import cho_factor, cho_solve
+    torch = _lib.torch_cuda()
+    B1 = _Bordered(n_fixed, n_cal)
+    fill_blocks(B1)
+    C_prime, delta = B1.schur(resid_fixed)
+    fl_prime = delta + float(mu_GP)
+    k = D.shape[1]
+    B2 = _Bordered(n_cal, k)
+    B2.data_block().copy_(C_prime)
+    B2.cross_block(0, k).copy_(torch.from_numpy(np.ascontiguousarray(D)).cuda())
+    S2, right = B2.schur(fl_prime)
+    left = (-S2).cpu().numpy()
+    X = cho_solve(cho_factor(left), right.cpu().numpy())
+    return np.dot(D, X), X
+
+
+def optimize_calibration(lwl0, lwl1, lwl_cal, fl_cal, fl_fixed, A, B, C, order=1, mu_GP=1.0):
+    """covariance.py:560-624.  A, B, C are the caller-filled covariance blocks (sigma^2 already on the diagonals of
+    A and B), numpy arrays or CUDA tensors."""
+    fl_cal = np.asarray(fl_cal, dtype=np.float64)
+    D = _chebyshev_design(lwl0, lwl1, lwl_cal, fl_cal, order)
+    A_d, B_d, C_d = _lib.dev_f64(A), _lib.dev_f64(B), _lib.dev_f64(C)
+    n_cal, n_fixed = A_d.shape[0], B_d.shape[0]
+
+    def fill(Bd):
+        Bd.data_block().copy_(B_d)
+        Bd.border_block(0, n_cal).copy_(A_d)
+        Bd.cross_block(0, n_cal).copy_(C_d.T)  # S(border a, data j) = C[a, j]
+
+    resid = _lib.dev_f64(np.asarray(fl_fixed, dtype=np.float64).flatten()) - float(mu_GP)
+    return _calibrate(fill, n_cal, n_fixed, resid, D, mu_GP)
+
+
+def optimize_calibration_static(wl0, wl1, wl_cal, fl_cal, sigma_cal, wl_fixed, fl_fixed, sigma_fixed, amp, l_f, order=1,
+                                mu_GP=1.0):
+    """covariance.py:627-711: fills A, B, C itself (zero relative velocity between the epochs)."""
+    fl_cal = np.asarray(fl_cal, dtype=np.float64)
+    D = _chebyshev_design(wl0, wl1, wl_cal, fl_cal, order)
+    lc, lf = _lib.dev_f64(wl_cal), _lib.dev_f64(wl_fixed)
+    sc, sf = _lib.dev_f64(sigma_cal), _lib.dev_f64(sigma_fixed)
+    n_cal, n_fixed = lc.numel(), lf.numel()
+
+    def fill(Bd):
+        _fill_data_block(Bd, [lf], [amp], [l_f], sf)
+        matrix_functions._fill_v11(Bd.border_block(0, n_cal), [lc], [amp], [l_f])
+        Bd.border_block(0, n_cal).diagonal().add_(sc * sc)
+        matrix_functions.fill_V12_sum(Bd.cross_block(0, n_cal), [lf], [lc], [amp], [l_f])
+
+    resid = _lib.dev_f64(np.asarray(fl_fixed, dtype=np.float64).flatten()) - float(mu_GP)
+    return _calibrate(fill, n_cal, n_fixed, resid, D, mu_GP)
+
+
+def cycle_calibration(wl, fl, sigma, amp_f, l_f, ncycles, order=1, limit_array=3, mu_GP=1.0, soften=1.0):
+    """covariance.py:714-748.  The reference calls optimize_calibration with the argument list of
+    optimize_calibration_static (a stale call that raises TypeError); the evident intent is implemented."""
+    wl, fl = np.asarray(wl, dtype=np.float64), np.asarray(fl, dtype=np.float64)
+    wl0, wl1 = np.min(wl), np.max(wl)
+    fl_out = np.copy(fl)
+    sigma = soften * np.asarray(sigma, dtype=np.float64)
+    for _ in range(ncycles):
+        for i in range(len(wl)):
+            wl_remain = np.delete(wl, i, axis=0)[0:limit_array]
+            fl_remain = np.delete(fl_out, i, axis=0)[0:limit_array]
+            sigma_remain = np.delete(sigma, i, axis=0)[0:limit_array]
+            fl_cor, _ = optimize_calibration_static(wl0, wl1, wl[i], fl_out[i], sigma[i], wl_remain.flatten(),
+                                                    fl_remain.flatten(), sigma_remain.flatten(), amp_f, l_f,
+                                                    order=order, mu_GP=mu_GP)
+            fl_out[i] = fl_cor
+    return fl_out

@@ -17,7 +17,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     return {name: np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
-            for name in ("fills", "orbits", "lnlike", "predict")}
+            for name in ("fills", "orbits", "lnlike", "predict", "calibration")}
 
 
 @pytest.fixture(scope="session")

@@ -136,7 +136,30 @@ def main():
     except NameError:
         out["predict_f_raises"] = "NameError"
     np.savez_compressed(os.path.join(HERE, "predict.npz"), **out)
-    for f in ("fills", "orbits", "lnlike", "predict"):
+
+    # ---------------------------------------------------------------- calibration (covariance.py:560-711)
+    out = {}
+    rng = np.random.default_rng(31)
+    ch = syn.make_chunk("SB1", 4, 60, 301)
+    lwl2d = ch["lwl"].reshape(4, 60); fl2d = ch["fl"].reshape(4, 60); sg2d = ch["sigma"].reshape(4, 60)
+    fl_cal = fl2d[0] * (1.0 + 0.03 * np.linspace(-1, 1, 60))           # a tilted epoch to calibrate
+    lwl_fixed, fl_fixed, sg_fixed = lwl2d[1:].flatten(), fl2d[1:].flatten(), sg2d[1:].flatten()
+    lwl0, lwl1 = lwl2d.min(), lwl2d.max()
+    amp, l = 0.1, 5.0
+    out.update(lwl_cal=lwl2d[0], fl_cal=fl_cal, sigma_cal=sg2d[0], lwl_fixed=lwl_fixed, fl_fixed=fl_fixed,
+               sigma_fixed=sg_fixed, lwl0=lwl0, lwl1=lwl1, amp=amp, l=l)
+    for order in (1, 2):
+        fl_cor, X = covariance.optimize_calibration_static(lwl0, lwl1, lwl2d[0], fl_cal, sg2d[0], lwl_fixed, fl_fixed,
+                                                           sg_fixed, amp, l, order=order, mu_GP=1.0)
+        out[f"static_o{order}_fl"], out[f"static_o{order}_X"] = fl_cor, X
+    A = np.empty((60, 60)); mf.fill_V11_f(A, lwl2d[0], amp, l); A[np.diag_indices_from(A)] += sg2d[0] ** 2
+    B = np.empty((180, 180)); mf.fill_V11_f(B, lwl_fixed, amp, l); B[np.diag_indices_from(B)] += sg_fixed ** 2
+    Cm = np.empty((60, 180)); mf.fill_V12_f(Cm, lwl2d[0], lwl_fixed, amp, l)
+    fl_cor, X = covariance.optimize_calibration(lwl0, lwl1, lwl2d[0], fl_cal, fl_fixed, A, B, Cm, order=1, mu_GP=1.0)
+    out["general_fl"], out["general_X"] = fl_cor, X
+    out["gp_fit"] = covariance.optimize_GP_f(lwl2d[1], fl2d[1], sg2d[1], 0.2, 8.0)
+    np.savez_compressed(os.path.join(HERE, "calibration.npz"), **out)
+    for f in ("fills", "orbits", "lnlike", "predict", "calibration"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")), "bytes")
 
 

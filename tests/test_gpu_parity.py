@@ -362,3 +362,34 @@ def test_sampler_chain_matches_oracle_at_visited_points(oracle, torch_cuda, tmp_
         ref, _ = oracle.farm_lnprob("SB2", np.concatenate([p_orb, p_GP]), chunks)
         assert rel_close(s.lnprobability[i], ref, LNLIKE_RTOL), (i, s.lnprobability[i], ref)
     assert s.naccepted >= 1
+
+
+def test_calibration_golden(golden, oracle, torch_cuda):
+    """covariance.optimize_calibration / _static (covariance.py:560-711) through two device Schur complements."""
+    from psoap_b200 import covariance
+    g = golden["calibration"]
+    amp, l = float(g["amp"]), float(g["l"])
+    args = (float(g["lwl0"]), float(g["lwl1"]), g["lwl_cal"], g["fl_cal"], g["sigma_cal"], g["lwl_fixed"], g["fl_fixed"],
+            g["sigma_fixed"], amp, l)
+    for order in (1, 2):
+        fl_cor, X = covariance.optimize_calibration_static(*args, order=order, mu_GP=1.0)
+        assert rel_close(X, g[f"static_o{order}_X"], 1e-7, 1e-10), (X, g[f"static_o{order}_X"])
+        assert rel_close(fl_cor, g[f"static_o{order}_fl"], 1e-8)
+    n_cal, n_fix = len(g["lwl_cal"]), len(g["lwl_fixed"])
+    A = np.empty((n_cal, n_cal)); oracle.fill_V11_f(A, g["lwl_cal"], amp, l); A[np.diag_indices_from(A)] += g["sigma_cal"] ** 2
+    B = np.empty((n_fix, n_fix)); oracle.fill_V11_f(B, g["lwl_fixed"], amp, l); B[np.diag_indices_from(B)] += g["sigma_fixed"] ** 2
+    C = np.empty((n_cal, n_fix)); oracle.fill_V12_f(C, g["lwl_cal"], g["lwl_fixed"], amp, l)
+    fl_cor, X = covariance.optimize_calibration(float(g["lwl0"]), float(g["lwl1"]), g["lwl_cal"], g["fl_cal"],
+                                                g["fl_fixed"], A, B, C, order=1, mu_GP=1.0)
+    assert rel_close(X, g["general_X"], 1e-7, 1e-10) and rel_close(fl_cor, g["general_fl"], 1e-8)
+    # Nelder-Mead hyper-parameter fit (covariance.py:408-424): same optimum as the reference's
+    lw2, fl2, sg2 = g["lwl_fixed"][:60], g["fl_fixed"][:60], g["sigma_fixed"][:60]
+    fit = covariance.optimize_GP_f(lw2, fl2, sg2, 0.2, 8.0)
+    assert np.all(np.abs(fit - g["gp_fit"]) <= 1e-3 * np.abs(g["gp_fit"])), (fit, g["gp_fit"])
+    # and the cycle driver runs and moves a deliberately tilted epoch back towards the others
+    wl = np.stack([g["lwl_cal"]] + [g["lwl_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
+    fl = np.stack([g["fl_cal"]] + [g["fl_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
+    sg = np.stack([g["sigma_cal"]] + [g["sigma_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
+    out = covariance.cycle_calibration(wl, fl, sg, amp, l, 1, order=1)
+    assert out.shape == fl.shape and np.all(np.isfinite(out))
+    assert np.abs(out[0] - fl[1]).mean() < np.abs(fl[0] - fl[1]).mean()

@@ -103,3 +103,21 @@ def test_predict(golden, oracle):
                                        amp[0], l[0], amp[1], l[1], amp[2], l[2])
     assert rel_close(mu, g["fghsum_mu"], 1e-12) and rel_close(Sig, g["fghsum_Sigma"], 1e-11, 1e-16)
     assert str(g["predict_f_raises"]) == "NameError"  # reference defect (covariance.py:38), documented
+
+
+def test_calibration_and_gp_fit(golden, oracle):
+    g = golden["calibration"]
+    args = (float(g["lwl0"]), float(g["lwl1"]), g["lwl_cal"], g["fl_cal"], g["sigma_cal"], g["lwl_fixed"], g["fl_fixed"],
+            g["sigma_fixed"], float(g["amp"]), float(g["l"]))
+    for order in (1, 2):
+        fl_cor, X = oracle.optimize_calibration_static(*args, order=order, mu_GP=1.0)
+        assert rel_close(X, g[f"static_o{order}_X"], 1e-9, 1e-12) and rel_close(fl_cor, g[f"static_o{order}_fl"], 1e-10)
+    n_cal, n_fix = len(g["lwl_cal"]), len(g["lwl_fixed"])
+    A = np.empty((n_cal, n_cal)); oracle.fill_V11_f(A, g["lwl_cal"], float(g["amp"]), float(g["l"]))
+    A[np.diag_indices_from(A)] += g["sigma_cal"] ** 2
+    B = np.empty((n_fix, n_fix)); oracle.fill_V11_f(B, g["lwl_fixed"], float(g["amp"]), float(g["l"]))
+    B[np.diag_indices_from(B)] += g["sigma_fixed"] ** 2
+    C = np.empty((n_cal, n_fix)); oracle.fill_V12_f(C, g["lwl_cal"], g["lwl_fixed"], float(g["amp"]), float(g["l"]))
+    fl_cor, X = oracle.optimize_calibration(float(g["lwl0"]), float(g["lwl1"]), g["lwl_cal"], g["fl_cal"],
+                                            g["fl_fixed"], A, B, C, order=1, mu_GP=1.0)
+    assert rel_close(X, g["general_X"], 1e-9, 1e-12) and rel_close(fl_cor, g["general_fl"], 1e-10)
