@@ -133,6 +133,13 @@ int psoap_farm_create(psoap_farm **farm, int model, int nchunks, const psoap_chu
  * results_dev: [nchunks] records; lnlike is -inf for |v| >= c (sample_parallel.py:186-187), negative
  * hyper-parameters, or a non-positive pivot. */
 int psoap_farm_lnprob(psoap_farm *farm, const double *p_dev, psoap_result *results_dev, void *stream);
+/* Batched variant (ensemble samplers): nprop proposals are evaluated by one graph launch; every
+ * (proposal, chunk) pair is an independent work item.  p_dev of psoap_farm_lnprob is then [nprop][n_params]
+ * contiguous and results_dev is [nprop][nchunks]. */
+size_t psoap_farm_workspace_bytes_batched(int nchunks, const int64_t *N, const int32_t *n_epochs, int nprop,
+                                          int nbranch);
+int psoap_farm_create_batched(psoap_farm **farm, int model, int nchunks, const psoap_chunk *chunks, int nprop,
+                              int nbranch, double mu_GP, void *workspace_dev, size_t workspace_bytes);
 int psoap_farm_launches_per_eval(const psoap_farm *farm);
 int psoap_farm_destroy(psoap_farm *farm);
 

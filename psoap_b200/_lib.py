@@ -60,6 +60,11 @@ SIGNATURES = {
     "psoap_farm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, c_i64_p, c_i32_p, ctypes.c_int]),
     "psoap_farm_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.POINTER(PsoapChunk),
                                          ctypes.c_int, ctypes.c_double, vp, ctypes.c_size_t]),
+    "psoap_farm_workspace_bytes_batched": (ctypes.c_size_t, [ctypes.c_int, c_i64_p, c_i32_p, ctypes.c_int,
+                                                             ctypes.c_int]),
+    "psoap_farm_create_batched": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(PsoapChunk), ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_double, vp, ctypes.c_size_t]),
     "psoap_farm_lnprob": (ctypes.c_int, [vp, vp, vp, vp]),
     "psoap_farm_launches_per_eval": (ctypes.c_int, [vp]),
     "psoap_farm_destroy": (ctypes.c_int, [vp]),

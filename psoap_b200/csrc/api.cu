@@ -478,17 +478,18 @@ extern "C" int psoap_schur_views(void* workspace, int64_t n, int64_t m, double**
 // ======================================================================================================
 // Chunk farm
 // ======================================================================================================
+constexpr int P_STRIDE = 32;  // doubles reserved per proposal in the parameter buffer
 struct psoap_farm {
-    int model = 0, ncomp = 0, norb = 0, nchunks = 0, nbranch = 0;
+    int model = 0, ncomp = 0, norb = 0, nchunks = 0, nprop = 1, nitems = 0, nbranch = 0;
     double mu = 1.0;
     std::vector<psoap_chunk> chunks;
     std::vector<FactorWs> branch_ws;
-    std::vector<std::vector<int>> branch_chunks;
-    double* p_buf = nullptr;          // [32] parameter vector the graph reads
-    double* results = nullptr;        // [nchunks][4]
-    double* vel = nullptr;            // per chunk [3 * n_epochs]
-    int* flags = nullptr;             // per chunk sentinel
-    OrbitDesc* descs = nullptr;       // device
+    std::vector<std::vector<int>> branch_items;
+    double* p_buf = nullptr;          // [nprop][P_STRIDE] parameter vectors the graph reads
+    double* results = nullptr;        // [nprop][nchunks][4]
+    double* vel = nullptr;            // per item [3 * n_epochs]
+    int* flags = nullptr;             // per item sentinel
+    OrbitDesc* descs = nullptr;       // device, per item
     std::vector<size_t> vel_off;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -500,36 +501,44 @@ struct psoap_farm {
 };
 
 namespace {
-size_t farm_small_bytes(int nchunks, const int32_t* n_epochs, std::vector<size_t>* vel_off) {
+// item = prop * nchunks + chunk
+size_t farm_small_bytes(int nchunks, int nprop, const int32_t* n_epochs, std::vector<size_t>* vel_off) {
+    const size_t nitems = (size_t)nchunks * nprop;
     size_t b = 0;
-    b += align_up(32 * 8, 256);                       // p_buf
-    b += align_up((size_t)nchunks * 4 * 8, 256);      // results
-    b += align_up((size_t)nchunks * 4, 256);          // flags
-    b += align_up((size_t)nchunks * sizeof(OrbitDesc), 256);
+    b += align_up((size_t)nprop * P_STRIDE * 8, 256);  // p_buf
+    b += align_up(nitems * 4 * 8, 256);                // results
+    b += align_up(nitems * 4, 256);                    // flags
+    b += align_up(nitems * sizeof(OrbitDesc), 256);
     size_t v = 0;
-    for (int i = 0; i < nchunks; ++i) {
-        if (vel_off) vel_off->push_back(v);
-        v += align_up((size_t)3 * n_epochs[i] * 8, 256);
-    }
+    for (int k = 0; k < nprop; ++k)
+        for (int i = 0; i < nchunks; ++i) {
+            if (vel_off) vel_off->push_back(v);
+            v += align_up((size_t)3 * n_epochs[i] * 8, 256);
+        }
     return b + v;
 }
 }  // namespace
 
 extern "C" {
 
-size_t psoap_farm_workspace_bytes(int nchunks, const int64_t* N, const int32_t* n_epochs, int nbranch) {
-    if (nchunks < 1 || !N || !n_epochs) return 0;
-    nbranch = std::max(1, std::min(nbranch, nchunks));
+size_t psoap_farm_workspace_bytes_batched(int nchunks, const int64_t* N, const int32_t* n_epochs, int nprop,
+                                          int nbranch) {
+    if (nchunks < 1 || nprop < 1 || !N || !n_epochs) return 0;
+    nbranch = std::max(1, std::min(nbranch, nchunks * nprop));
     int64_t nmax = 0;
     for (int i = 0; i < nchunks; ++i) nmax = std::max(nmax, N[i]);
-    return farm_small_bytes(nchunks, n_epochs, nullptr) + (size_t)nbranch * factor_ws_bytes(padded_dim(nmax));
+    return farm_small_bytes(nchunks, nprop, n_epochs, nullptr) + (size_t)nbranch * factor_ws_bytes(padded_dim(nmax));
+}
+size_t psoap_farm_workspace_bytes(int nchunks, const int64_t* N, const int32_t* n_epochs, int nbranch) {
+    return psoap_farm_workspace_bytes_batched(nchunks, N, n_epochs, 1, nbranch);
 }
 
-int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chunk* chunks, int nbranch, double mu_GP,
-                      void* workspace, size_t workspace_bytes) {
-    if (!out || model < 1 || model > 5 || nchunks < 1 || !chunks || !workspace || ((uintptr_t)workspace & 255))
+int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const psoap_chunk* chunks, int nprop,
+                              int nbranch, double mu_GP, void* workspace, size_t workspace_bytes) {
+    if (!out || model < 1 || model > 5 || nchunks < 1 || nprop < 1 || !chunks || !workspace || ((uintptr_t)workspace & 255))
         return fail(PSOAP_ERR_ARG, "psoap_farm_create: bad arguments");
-    nbranch = std::max(1, std::min(nbranch, nchunks));
+    const int nitems = nchunks * nprop;
+    nbranch = std::max(1, std::min(nbranch, nitems));
     std::vector<int64_t> Ns(nchunks);
     std::vector<int32_t> nes(nchunks);
     for (int i = 0; i < nchunks; ++i) {
@@ -539,50 +548,53 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
         Ns[i] = chunks[i].N;
         nes[i] = chunks[i].n_epochs;
     }
-    if (workspace_bytes < psoap_farm_workspace_bytes(nchunks, Ns.data(), nes.data(), nbranch))
+    if (workspace_bytes < psoap_farm_workspace_bytes_batched(nchunks, Ns.data(), nes.data(), nprop, nbranch))
         return fail(PSOAP_ERR_WORKSPACE, "psoap_farm_create: workspace too small");
     int rc = set_kernel_attributes();
     if (rc) return rc;
 
     psoap_farm* f = new psoap_farm();
     f->model = model; f->ncomp = model_ncomp(model); f->norb = model_norb(model);
-    f->nchunks = nchunks; f->nbranch = nbranch; f->mu = mu_GP;
+    f->nchunks = nchunks; f->nprop = nprop; f->nitems = nitems; f->nbranch = nbranch; f->mu = mu_GP;
     f->chunks.assign(chunks, chunks + nchunks);
     char* p = (char*)workspace;
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
-    f->p_buf = (double*)take(32 * 8);
-    f->results = (double*)take((size_t)nchunks * 4 * 8);
-    f->flags = (int*)take((size_t)nchunks * 4);
-    f->descs = (OrbitDesc*)take((size_t)nchunks * sizeof(OrbitDesc));
-    farm_small_bytes(nchunks, nes.data(), &f->vel_off);
+    f->p_buf = (double*)take((size_t)nprop * P_STRIDE * 8);
+    f->results = (double*)take((size_t)nitems * 4 * 8);
+    f->flags = (int*)take((size_t)nitems * 4);
+    f->descs = (OrbitDesc*)take((size_t)nitems * sizeof(OrbitDesc));
+    const size_t small = farm_small_bytes(nchunks, nprop, nes.data(), &f->vel_off);
     f->vel = (double*)p;
-    p += f->vel_off.back() + align_up((size_t)3 * nes.back() * 8, 256);
+    p = (char*)workspace + small;
     int64_t nmax = *std::max_element(Ns.begin(), Ns.end());
     const size_t per_branch = factor_ws_bytes(padded_dim(nmax));
     f->branch_ws.resize(nbranch);
     for (int b = 0; b < nbranch; ++b) carve_factor_ws(p + (size_t)b * per_branch, padded_dim(nmax), &f->branch_ws[b], true);
 
-    // orbit descriptors
-    std::vector<OrbitDesc> hd(nchunks);
-    for (int i = 0; i < nchunks; ++i) {
-        hd[i].dates = chunks[i].dates;
-        hd[i].vel = (double*)((char*)f->vel + f->vel_off[i]);
-        hd[i].flag = f->flags + i;
-        hd[i].n_epochs = chunks[i].n_epochs;
+    // orbit descriptors, one per (proposal, chunk)
+    std::vector<OrbitDesc> hd(nitems);
+    for (int it = 0; it < nitems; ++it) {
+        const int ci = it % nchunks, k = it / nchunks;
+        hd[it].dates = chunks[ci].dates;
+        hd[it].vel = (double*)((char*)f->vel + f->vel_off[it]);
+        hd[it].flag = f->flags + it;
+        hd[it].n_epochs = chunks[ci].n_epochs;
+        hd[it].p_off = k * P_STRIDE;
     }
-    cudaError_t e = cudaMemcpy(f->descs, hd.data(), (size_t)nchunks * sizeof(OrbitDesc), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(f->descs, hd.data(), (size_t)nitems * sizeof(OrbitDesc), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { delete f; return fail(PSOAP_ERR_CUDA, std::string("farm descs: ") + cudaGetErrorString(e)); }
 
-    // LPT (longest processing time first) assignment of chunks to branches by N^3
-    std::vector<int> order(nchunks);
+    // LPT (longest processing time first) assignment of work items to branches by N^3
+    std::vector<int> order(nitems);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Ns[a] > Ns[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Ns[a % nchunks] > Ns[b % nchunks]; });
     std::vector<double> load(nbranch, 0.0);
-    f->branch_chunks.assign(nbranch, {});
-    for (int idx : order) {
+    f->branch_items.assign(nbranch, {});
+    for (int it : order) {
         int b = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        f->branch_chunks[b].push_back(idx);
-        load[b] += (double)Ns[idx] * Ns[idx] * Ns[idx];
+        f->branch_items[b].push_back(it);
+        const double n = (double)Ns[it % nchunks];
+        load[b] += n * n * n;
     }
 
     // capture the whole evaluation into one CUDA graph
@@ -602,30 +614,30 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
     const int64_t before = g_launches.load();
     e = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { psoap_farm_destroy(f); return fail(PSOAP_ERR_CUDA, std::string("begin capture: ") + cudaGetErrorString(e)); }
-    orbit_farm_kernel<<<nchunks, 64, 0, s0>>>(model, f->p_buf, f->descs);
+    orbit_farm_kernel<<<nitems, 64, 0, s0>>>(model, f->p_buf, f->descs);
     ++g_launches;
     cudaEventRecord(f->events[nbranch], s0);
-    GpParams gp;
-    gp.dev = f->p_buf + f->norb;
-    for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
     rc = PSOAP_OK;
     const char* la_env = getenv("PSOAP_FARM_LOOKAHEAD");
     const bool lookahead = la_env ? (atoi(la_env) != 0) : (nbranch < 8);
     for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
         cudaStream_t sb = f->streams[b];
         cudaStreamWaitEvent(sb, f->events[nbranch], 0);
-        for (int idx : f->branch_chunks[b]) {
-            const psoap_chunk& ch = f->chunks[idx];
+        for (int it : f->branch_items[b]) {
+            const psoap_chunk& ch = f->chunks[it % nchunks];
+            GpParams gp;
+            gp.dev = f->p_buf + (size_t)(it / nchunks) * P_STRIDE + f->norb;
+            for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
             ZSource zs;
             zs.lwl[0] = ch.lwl; zs.lwl[1] = nullptr; zs.lwl[2] = nullptr;
-            zs.epoch = ch.epoch; zs.vel = hd[idx].vel; zs.n_epochs = ch.n_epochs; zs.shift = 1;
+            zs.epoch = ch.epoch; zs.vel = hd[it].vel; zs.n_epochs = ch.n_epochs; zs.shift = 1;
             FactorWs ws = f->branch_ws[b];
             ws.Nt = padded_dim(ch.N);
             Lanes ln;
             ln.main = sb;
             ln.side = lookahead ? f->side_streams[b] : nullptr;
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
-            rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + idx, f->results + 4 * idx);
+            rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + it, f->results + 4 * it);
             if (rc) break;
         }
         cudaEventRecord(f->events[b], sb);
@@ -642,14 +654,21 @@ int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chun
     return PSOAP_OK;
 }
 
+int psoap_farm_create(psoap_farm** out, int model, int nchunks, const psoap_chunk* chunks, int nbranch, double mu_GP,
+                      void* workspace, size_t workspace_bytes) {
+    return psoap_farm_create_batched(out, model, nchunks, chunks, 1, nbranch, mu_GP, workspace, workspace_bytes);
+}
+
 int psoap_farm_lnprob(psoap_farm* f, const double* p_dev, psoap_result* results_dev, void* stream) {
     if (!f || !p_dev || !results_dev) return fail(PSOAP_ERR_ARG, "psoap_farm_lnprob: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int np = f->norb + 2 * f->ncomp;
-    CUDA_TRY(cudaMemcpyAsync(f->p_buf, p_dev, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
+    // p_dev: [nprop][np] contiguous -> [nprop][P_STRIDE]
+    CUDA_TRY(cudaMemcpy2DAsync(f->p_buf, P_STRIDE * 8, p_dev, (size_t)np * 8, (size_t)np * 8, f->nprop,
+                               cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaGraphLaunch(f->exec, st));
     g_launches += f->launches;
-    CUDA_TRY(cudaMemcpyAsync(results_dev, f->results, (size_t)f->nchunks * sizeof(psoap_result), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(results_dev, f->results, (size_t)f->nitems * sizeof(psoap_result), cudaMemcpyDeviceToDevice, st));
     return PSOAP_OK;
 }
 

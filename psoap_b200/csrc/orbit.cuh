@@ -106,15 +106,17 @@ __global__ void orbit_kernel(int model, const double* __restrict__ p, const doub
 }
 
 // Chunk farm: block b evaluates chunk b's epochs (every chunk carries its own date vector, data.py:126).
+// One descriptor per (chunk, proposal) work item; p_off selects the proposal's parameter vector.
 struct OrbitDesc {
     const double* dates;
     double* vel;
     int* flag;
     int n_epochs;
+    int p_off;
 };
 __global__ void orbit_farm_kernel(int model, const double* __restrict__ p, const OrbitDesc* __restrict__ descs) {
     const OrbitDesc d = descs[blockIdx.x];
-    orbit_block(model, p, d.dates, d.n_epochs, d.vel, d.flag, 1);
+    orbit_block(model, p + d.p_off, d.dates, d.n_epochs, d.vel, d.flag, 1);
 }
 
 }  // namespace psoap

@@ -41,10 +41,12 @@ class ChunkFarm:
     rank/world_size: static partition of the chunks over GPUs; process_group: torch.distributed group (or None).
     """
 
-    def __init__(self, model, chunks, mu_GP=1.0, soften=1.0, nbranch=32, rank=0, world_size=1, process_group=None):
+    def __init__(self, model, chunks, mu_GP=1.0, soften=1.0, nbranch=32, rank=0, world_size=1, process_group=None,
+                 n_proposals=1):
         lib = _lib.load()
         torch = _lib.torch_cuda()
         self.model = model
+        self.n_proposals = int(n_proposals)
         self.n_chunks = len(chunks)
         self.n_params = _lib.N_ORB[model] + 2 * _lib.NCOMP[model]
         self.rank, self.world_size, self.group = rank, world_size, process_group
@@ -90,20 +92,21 @@ class ChunkFarm:
         torch.cuda.synchronize()
         self.Ns = Ns
         self._farm = _lib.vp(None)
-        self._results = torch.zeros((max(1, len(self.mine)), 4), dtype=torch.float64, device="cuda")
-        self._p_dev = torch.zeros(self.n_params, dtype=torch.float64, device="cuda")
-        self._p_pin = torch.zeros(self.n_params, dtype=torch.float64).pin_memory()
-        self._lnl_all = torch.zeros(self.n_chunks, dtype=torch.float64, device="cuda")
-        self._lnl_pin = torch.zeros(self.n_chunks, dtype=torch.float64).pin_memory()
+        K = self.n_proposals
+        self._results = torch.zeros((K, max(1, len(self.mine)), 4), dtype=torch.float64, device="cuda")
+        self._p_dev = torch.zeros((K, self.n_params), dtype=torch.float64, device="cuda")
+        self._p_pin = torch.zeros((K, self.n_params), dtype=torch.float64).pin_memory()
+        self._lnl_all = torch.zeros((K, self.n_chunks), dtype=torch.float64, device="cuda")
+        self._lnl_pin = torch.zeros((K, self.n_chunks), dtype=torch.float64).pin_memory()
         self._mine_idx = torch.tensor(self.mine, dtype=torch.int64, device="cuda")
         self.launches_per_eval = 0
         if self.mine:
-            nb = max(1, min(nbranch, len(self.mine)))
-            nbytes = lib.psoap_farm_workspace_bytes(len(self.mine), (ctypes.c_int64 * len(Ns))(*Ns),
-                                                    (ctypes.c_int32 * len(nes))(*nes), nb)
+            nb = max(1, min(nbranch, len(self.mine) * K))
+            nbytes = lib.psoap_farm_workspace_bytes_batched(len(self.mine), (ctypes.c_int64 * len(Ns))(*Ns),
+                                                            (ctypes.c_int32 * len(nes))(*nes), K, nb)
             self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
-            _lib.check(lib.psoap_farm_create(ctypes.byref(self._farm), _lib.MODELS[model], len(self.mine), descs, nb,
-                                             float(mu_GP), _lib.ptr(self._ws), nbytes))
+            _lib.check(lib.psoap_farm_create_batched(ctypes.byref(self._farm), _lib.MODELS[model], len(self.mine),
+                                                     descs, K, nb, float(mu_GP), _lib.ptr(self._ws), nbytes))
             self.launches_per_eval = lib.psoap_farm_launches_per_eval(self._farm)
 
     # -- per-rank work --------------------------------------------------------------------------------
@@ -117,31 +120,35 @@ class ChunkFarm:
         return self._data_bytes
 
     def lnprob_device(self, p_dev):
-        """Evaluate this rank's chunks for the device parameter vector p_dev (full registered vector, orbital
-        then GP, utils.py:4-8).  Asynchronous; returns the [n_mine, 4] result tensor (lnlike, logdet, quad, info)."""
+        """Evaluate this rank's chunks for the device parameter vector(s) p_dev ([n_params], or
+        [n_proposals, n_params]; full registered vector, orbital then GP, utils.py:4-8).  Asynchronous; returns the
+        [n_proposals, n_mine, 4] result tensor (lnlike, logdet, quad, info)."""
         if self.mine:
             _lib.check(_lib.load().psoap_farm_lnprob(self._farm, _lib.ptr(p_dev), _lib.ptr(self._results),
                                                      _lib.stream_ptr()))
         return self._results
 
     def chunk_lnlikes_device(self, p_dev):
-        """All chunks' log-likelihoods for a DEVICE parameter vector, as a device tensor [n_chunks]; asynchronous
-        (no host synchronisation).  With world_size > 1 it ends with the one collective of the path."""
+        """All chunks' log-likelihoods for DEVICE parameter vector(s), as a device tensor [n_proposals, n_chunks]
+        ([n_chunks] when n_proposals == 1); asynchronous (no host synchronisation).  With world_size > 1 it ends
+        with the one collective of the path."""
         res = self.lnprob_device(p_dev)
         self._lnl_all.zero_()
         if self.mine:
-            self._lnl_all.index_copy_(0, self._mine_idx, res[:len(self.mine), 0])
+            self._lnl_all.index_copy_(1, self._mine_idx, res[:, :len(self.mine), 0])
         if self.world_size > 1:
             self._allreduce(self._lnl_all)
-        return self._lnl_all
+        return self._lnl_all[0] if self.n_proposals == 1 else self._lnl_all
 
     def chunk_lnlikes(self, p):
-        """Same for a HOST parameter vector p (staged through pinned memory)."""
+        """Same for HOST parameter vector(s) p (staged through pinned memory)."""
         torch = _lib.torch_cuda()
-        p = np.asarray(p, dtype=np.float64)
-        if p.shape != (self.n_params,):
-            raise ValueError("p must hold the %d registered parameters of %s" % (self.n_params, self.model))
-        self._p_pin.copy_(torch.from_numpy(p))
+        p = np.asarray(p, dtype=np.float64).reshape(-1, self.n_params) if np.size(p) == self.n_proposals * self.n_params \
+            else None
+        if p is None:
+            raise ValueError("p must hold %d x %d registered parameters of %s"
+                             % (self.n_proposals, self.n_params, self.model))
+        self._p_pin.copy_(torch.from_numpy(np.ascontiguousarray(p)))
         self._p_dev.copy_(self._p_pin, non_blocking=True)
         return self.chunk_lnlikes_device(self._p_dev)
 
@@ -153,8 +160,14 @@ class ChunkFarm:
     def lnprob(self, p):
         """sample_parallel.py:371-390 without the prior: sum over chunks, in chunk order, of the per-chunk lnlike."""
         lnl = self.chunk_lnlikes(p)
-        self._lnl_pin.copy_(lnl, non_blocking=False)
-        return float(np.sum(self._lnl_pin.numpy()))
+        self._lnl_pin.copy_(self._lnl_all, non_blocking=False)
+        sums = np.sum(self._lnl_pin.numpy(), axis=1)
+        return float(sums[0]) if self.n_proposals == 1 else sums
+
+    def lnprob_many(self, P):
+        """Ensemble evaluation: P is [n_proposals, n_params]; one graph launch evaluates every
+        (proposal, chunk) pair; returns the n_proposals summed log-likelihoods."""
+        return np.atleast_1d(self.lnprob(P))
 
     def close(self):
         if self._farm:

@@ -386,10 +386,35 @@ def test_calibration_golden(golden, oracle, torch_cuda):
     lw2, fl2, sg2 = g["lwl_fixed"][:60], g["fl_fixed"][:60], g["sigma_fixed"][:60]
     fit = covariance.optimize_GP_f(lw2, fl2, sg2, 0.2, 8.0)
     assert np.all(np.abs(fit - g["gp_fit"]) <= 1e-3 * np.abs(g["gp_fit"])), (fit, g["gp_fit"])
-    # and the cycle driver runs and moves a deliberately tilted epoch back towards the others
+    # the cycle driver (covariance.py:714-748, with the evident call) against the same loop over the oracle
     wl = np.stack([g["lwl_cal"]] + [g["lwl_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
     fl = np.stack([g["fl_cal"]] + [g["fl_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
     sg = np.stack([g["sigma_cal"]] + [g["sigma_fixed"][60 * k:60 * (k + 1)] for k in range(3)])
     out = covariance.cycle_calibration(wl, fl, sg, amp, l, 1, order=1)
-    assert out.shape == fl.shape and np.all(np.isfinite(out))
-    assert np.abs(out[0] - fl[1]).mean() < np.abs(fl[0] - fl[1]).mean()
+    ref = np.copy(fl)
+    for i in range(4):
+        rem = lambda a: np.delete(a, i, axis=0)[0:3].flatten()
+        ref[i], _ = oracle.optimize_calibration_static(wl.min(), wl.max(), wl[i], ref[i], sg[i], rem(wl), rem(ref),
+                                                       rem(sg), amp, l, order=1, mu_GP=1.0)
+    assert out.shape == fl.shape and rel_close(out, ref, 1e-7)
+
+
+def test_farm_many_proposals(oracle, torch_cuda):
+    """Ensemble evaluation: K proposals x all chunks in one graph launch equal K single evaluations / the oracle."""
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import ChunkFarm
+    chunks = [synthetic.make_chunk("SB2", 4, 35 + 11 * i, seed=900 + i, mask_frac=0.03 * (i % 2)) for i in range(4)]
+    p = synthetic.default_params("SB2")
+    P = np.stack([p * (1.0 + 0.01 * k * np.array([0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1])) for k in range(5)])
+    P[3, 1] = 4e5   # |v| >= c for proposal 3 only
+    farm = ChunkFarm("SB2", chunks, n_proposals=5, nbranch=6)
+    got = farm.lnprob_many(P)
+    per = farm.chunk_lnlikes(P).cpu().numpy()
+    assert got.shape == (5,) and per.shape == (5, 4)
+    for k in range(5):
+        ref, ref_vec = oracle.farm_lnprob("SB2", P[k], chunks)
+        if k == 3:
+            assert got[k] == -np.inf and ref == -np.inf
+        else:
+            assert rel_close(got[k], ref, LNLIKE_RTOL) and rel_close(per[k], ref_vec, LNLIKE_RTOL), (k, got[k], ref)
+    farm.close()
