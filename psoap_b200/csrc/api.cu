@@ -690,19 +690,19 @@ int psoap_farm_destroy(psoap_farm* f) {
 // rank-K update (K = 128 or 256) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
 // stream.  flops_per_launch is the algorithmic count K * m * (m + 128) (2 flops per multiply-add, lower tiles).
 int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
-    if (m < NB || m % NB || reps < 1 || !avg_ms_out || (K != NB && K != 2 * NB))
+    if (m < NB || m % NB || reps < 1 || !avg_ms_out || K < NB || K % NB || K > 2048)
         return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
     int rc = set_kernel_attributes();
     if (rc) return rc;
     double *W = nullptr, *P = nullptr, *y = nullptr, *r = nullptr;
     CUDA_TRY(cudaMalloc(&W, (size_t)m * m * 8));
-    CUDA_TRY(cudaMalloc(&P, (size_t)m * 2 * NB * 8));
+    CUDA_TRY(cudaMalloc(&P, (size_t)m * K * 8));
     CUDA_TRY(cudaMalloc(&y, NB * 8));
     CUDA_TRY(cudaMalloc(&r, (size_t)m * 8));
     CUDA_TRY(cudaMemset(W, 0, (size_t)m * m * 8));
     CUDA_TRY(cudaMemset(y, 0, NB * 8));
     CUDA_TRY(cudaMemset(r, 0, (size_t)m * 8));
-    std::vector<double> hp((size_t)m * 2 * NB);
+    std::vector<double> hp((size_t)m * K);
     for (size_t i = 0; i < hp.size(); ++i) hp[i] = 1e-3 * (double)((i * 2654435761u) % 1000) - 0.5;
     CUDA_TRY(cudaMemcpy(P, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice));
     cudaStream_t st;
