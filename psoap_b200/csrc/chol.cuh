@@ -30,7 +30,7 @@ __device__ __forceinline__ void kahan_add(double* sum, double* comp, double x) {
 // One __syncthreads per step; the published column/row are double buffered.
 // ------------------------------------------------------------------------------------------------------
 constexpr int XS = NB + 1;
-constexpr int POTRF_SMEM = (NB * XS + 2 * NB + 2 * NB + NB + NB + 256 + 4) * 8;
+constexpr int POTRF_SMEM = (NB * XS + 2 * NB + 2 * NB + NB + NB + 512 + 4) * 8;
 
 __global__ void __launch_bounds__(256, 1)
 potrf_diag_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, double* __restrict__ Linv,
@@ -169,6 +169,7 @@ potrf_diag_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, dou
 
 // Common tail of the diagonal-block kernels: logdet and pivot check, y_k = X r_k and its norm, L_kk^-1 to
 // global memory, Kahan accumulation across panels, and the final result record on the last panel.
+template <int NT = 256>
 __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const double* Xs, const double* dval,
                                                const double* rs, double* red, double* __restrict__ Linv,
                                                double* __restrict__ yk, double* __restrict__ acc,
@@ -184,7 +185,7 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
     }
     red[tid] = lg;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = NT / 2; s > 0; s >>= 1) {
         if (tid < s) red[tid] += red[tid + s];
         __syncthreads();
     }
@@ -197,7 +198,7 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
     }
     red[tid] = y * y;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = NT / 2; s > 0; s >>= 1) {
         if (tid < s) red[tid] += red[tid + s];
         __syncthreads();
     }
@@ -206,11 +207,11 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
     int* redi = reinterpret_cast<int*>(red);
     redi[tid] = bad;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = NT / 2; s > 0; s >>= 1) {
         if (tid < s) redi[tid] = min(redi[tid], redi[tid + s]);
         __syncthreads();
     }
-    for (int e = tid; e < NB * NB; e += 256) {
+    for (int e = tid; e < NB * NB; e += NT) {
         const int r = e & (NB - 1), c = e >> 7;
         Linv[e] = Xs[c * XS + r];
     }
@@ -230,133 +231,7 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
 }
 
 // ------------------------------------------------------------------------------------------------------
-// potrf_diag2: same algorithm and register layout as potrf_diag, restructured so the 128 dependent pivots see
-// a short chain.  Within step j every thread first computes only the entries the NEXT step publishes (column
-// j+1, row j+1, and the pivot owner its reciprocal square root), publishes them, and all threads meet at the
-// barrier; the bulk of the rank-1 update is issued after the barrier, overlapping the next step's loads.
-// The reciprocal square root is computed once per step by the pivot owner instead of by all 256 threads.
-// ------------------------------------------------------------------------------------------------------
-template <int NQ>
-__device__ __forceinline__ void potrf_publish_next(double (&M)[8][8], const double (&li)[8], const double (&w)[8],
-                                                   int ti, int tc, int jrn, bool special_col, int jq_cur, double* cbn,
-                                                   double* rbn, double* scn) {
-    if (tc == jrn) {
-#pragma unroll
-        for (int p = NQ; p < 8; ++p) cbn[ti + 16 * p] = fma(-li[p], w[NQ], M[p][NQ]);
-    }
-    if (ti == jrn) {
-#pragma unroll
-        for (int q = 0; q <= NQ; ++q) {
-            const double base = (special_col && q == jq_cur) ? 0.0 : M[NQ][q];
-            rbn[tc + 16 * q] = fma(-li[NQ], w[q], base);
-        }
-        if (tc == jrn) {
-            const double d = fma(-li[NQ], w[NQ], M[NQ][NQ]);
-            scn[0] = d;
-            scn[1] = rsqrt(d);
-        }
-    }
-}
-
-template <int JQ>
-__device__ __forceinline__ void potrf2_block_steps(double (&M)[8][8], int ti, int tc, int tid, double* Xs, double* colb,
-                                                   double* rowb, double* scal, double* dval) {
-#pragma unroll 1
-        for (int jr = 0; jr < 16; ++jr) {
-            const int j = 16 * JQ + jr;
-            const double* cb = colb + (j & 1) * NB;
-            const double* rb = rowb + (j & 1) * NB;
-            const double inv = scal[(j & 1) * 2 + 1];
-            if (tid == 0) dval[j] = scal[(j & 1) * 2];
-            if (tid < NB) {  // row j of X = L^-1 is final
-                const int c = tid;
-                Xs[c * XS + j] = (c < j) ? rb[c] * inv : ((c == j) ? inv : 0.0);
-            }
-            double li[8], w[8];
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                if (p < JQ) { li[p] = 0.0; continue; }
-                const int i = ti + 16 * p;
-                li[p] = (p > JQ || ti > jr) ? cb[i] * inv : 0.0;
-            }
-            const bool special = (tc == jr);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = tc + 16 * q;
-                if (q > JQ) w[q] = cb[c] * inv;
-                else if (q < JQ) w[q] = rb[c] * inv;
-                else w[q] = (tc > jr) ? cb[c] * inv : ((tc < jr) ? rb[c] * inv : inv);
-            }
-            // ---- what step j+1 needs, first
-            if (j < NB - 1) {
-                double* cbn = colb + ((j + 1) & 1) * NB;
-                double* rbn = rowb + ((j + 1) & 1) * NB;
-                double* scn = scal + ((j + 1) & 1) * 2;
-                if (jr < 15) potrf_publish_next<JQ>(M, li, w, ti, tc, jr + 1, special, JQ, cbn, rbn, scn);
-                else potrf_publish_next<(JQ < 7 ? JQ + 1 : 7)>(M, li, w, ti, tc, 0, special, JQ, cbn, rbn, scn);
-            }
-            __syncthreads();
-            // ---- bulk of the rank-1 update
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-#pragma unroll
-                for (int p = (q > JQ ? q : JQ); p < 8; ++p) {
-                    const double base = (special && q == JQ) ? 0.0 : M[p][q];
-                    M[p][q] = fma(-li[p], w[q], base);
-                }
-            }
-        }
-    }
-
-__global__ void __launch_bounds__(256, 1)
-potrf_diag2_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, double* __restrict__ Linv,
-                   double* __restrict__ rvec, double* __restrict__ yk, double* __restrict__ acc,
-                   int* __restrict__ info, const int* __restrict__ sentinel, int is_last,
-                   double* __restrict__ result) {
-    extern __shared__ double sm[];
-    double* Xs = sm;                  // Xs[c*XS + r] = X[r][c], X = L^-1
-    double* colb = Xs + NB * XS;      // [2][NB]
-    double* rowb = colb + 2 * NB;     // [2][NB]
-    double* dval = rowb + 2 * NB;     // [NB] pivots d_j
-    double* rs = dval + NB;           // [NB] residual segment
-    double* red = rs + NB;            // [256]
-    double* scal = red + 256;         // [2][2]: pivot d_j and d_j^-1/2
-    const int tid = threadIdx.x;
-    const int ti = tid & 15, tc = tid >> 4;
-    const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
-
-    double M[8][8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            if (p < q) { M[p][q] = 0.0; continue; }
-            const int i = ti + 16 * p, c = tc + 16 * q;
-            M[p][q] = (i >= c) ? A[i + (int64_t)c * ld] : 0.0;
-        }
-    if (tid < NB) rs[tid] = rvec[kb * NB + tid];
-    // publish step 0
-    if (tc == 0) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) colb[ti + 16 * p] = M[p][0];
-        if (ti == 0) { scal[0] = M[0][0]; scal[1] = rsqrt(M[0][0]); }
-    }
-    __syncthreads();
-
-    potrf2_block_steps<0>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<1>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<2>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<3>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<4>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<5>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<6>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    potrf2_block_steps<7>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    __syncthreads();
-    potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// potrf_diag3: same algorithm and register layout again, with the per-step instruction count cut to the bone
+// potrf_diag3: same algorithm and register layout as potrf_diag, with the per-step instruction count cut down
 // (the step is issue bound: 8 warps x ~130 instructions on one SM).  The owners of column j scale it BEFORE
 // publishing (the pivot travels to them by warp shuffle, they sit in one half-warp), rows that are already
 // finished are published as zeros, so a consumer's step is 16 shared loads, <= 36 DFMA and a handful of
@@ -439,7 +314,7 @@ potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     double* dval = rowb + 2 * NB;     // [NB] pivots d_j
     double* rs = dval + NB;           // [NB] residual segment
     double* red = rs + NB;            // [256]
-    double* scal = red + 256;         // [2][2]: pivot d_j and d_j^-1/2
+    double* scal = red + 512;         // [2][2]: pivot d_j and d_j^-1/2
     const int tid = threadIdx.x;
     const int ti = tid & 15, tc = tid >> 4;
     const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
