@@ -22,25 +22,31 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size"]
 
 
-def launches(path):
+def launches(path, n_sms=148):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     hdr, data = rows[hi], rows[hi + 1:]
-    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    agg = collections.defaultdict(list)
+    ki, vi, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Grid Size")
+    agg, smt = collections.defaultdict(list), collections.defaultdict(float)
     for r in data:
         if len(r) <= vi:
             continue
         v = float(r[vi].replace(",", ""))
         v = v / 1000 if r[ui] == "ns" else (v * 1000 if r[ui] == "ms" else v)
-        agg[r[ki].split("(")[0]].append(v)
-    tot = sum(sum(v) for v in agg.values())
+        name = r[ki].split("(")[0]
+        agg[name].append(v)
+        grid = 1
+        for g in r[gi].strip("()").split(","):
+            grid *= int(g)
+        smt[name] += v * min(1.0, grid / n_sms)   # device time weighted by the fraction of SMs the grid can occupy
+    tot, tot_sm = sum(sum(v) for v in agg.values()), sum(smt.values())
     print("# per-kernel device time from %s (ncu replays each launch alone and cold: compare SHARES)" % path)
-    print("%-52s %7s %12s %7s %10s %10s %10s" % ("kernel", "n", "total_ms", "share", "avg_us", "min_us", "max_us"))
+    print("# sm_share weights every launch by min(1, CTAs / %d SMs): a 1-CTA kernel occupies 1/%d of the GPU" % (n_sms, n_sms))
+    print("%-44s %7s %11s %7s %9s %9s %9s %9s" % ("kernel", "n", "total_ms", "share", "sm_share", "avg_us", "min_us", "max_us"))
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        print("%-52s %7d %12.3f %6.1f%% %10.2f %10.2f %10.2f" % (k[:52], len(v), sum(v) / 1000, 100 * sum(v) / tot,
-                                                                 sum(v) / len(v), min(v), max(v)))
-    print("%-52s %7d %12.3f" % ("TOTAL", sum(len(v) for v in agg.values()), tot / 1000))
+        print("%-44s %7d %11.3f %6.1f%% %8.1f%% %9.2f %9.2f %9.2f" % (k[:44], len(v), sum(v) / 1000, 100 * sum(v) / tot,
+                                                                    100 * smt[k] / tot_sm, sum(v) / len(v), min(v), max(v)))
+    print("%-44s %7d %11.3f" % ("TOTAL", sum(len(v) for v in agg.values()), tot / 1000))
 
 
 def report(path):
