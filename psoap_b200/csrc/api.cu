@@ -52,6 +52,7 @@ int g_num_sms = 148;
 int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
 int g_potrf_version = 3;
+int g_pf_mode = 2;
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
@@ -68,6 +69,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = atoi(c);
+        if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -153,7 +155,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         const int R = T_total - row0;
         SyrkSrc src;
         src.W = W; src.ld = ld; src.row0 = row0; src.kbeg = kbeg_of(q); src.kend = kend;
-        src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = ncol1;
+        src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = ncol1; src.pf_mode = g_pf_mode;
         const int ntiles = syrk_ntiles(R, part, ncol1);
         const int nres = part == 2 ? 0 : R;
         if (ntiles + nres == 0) return;
@@ -161,7 +163,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         // continuously and the high-priority side stream (next pair's potrf/trsm) is scheduled into them.
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
-        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, ws.y + (int64_t)ykb * NB, ws.rvec, res_col0);
+        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)ykb * NB, ws.rvec, res_col0);
         ++g_launches;
     };
     const int npairs = (T_elim + 1) / 2;
@@ -709,10 +711,11 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     const int R = (int)(m / NB), ntiles = R * (R + 1);
     SyrkSrc src;
     src.W = W; src.ld = m; src.row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
+    src.pf_mode = g_pf_mode;
     const int nctas = persistent_ctas(ntiles);
-    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r, 0); ++g_launches; }
+    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0); ++g_launches; }
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, y, r, 0); ++g_launches; }
+    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0); ++g_launches; }
     cudaEventRecord(e1, st);
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;

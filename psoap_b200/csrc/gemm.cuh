@@ -60,6 +60,9 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void tma_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
 
 struct TileDesc {
     const double* Ai;  // [128 rows, k] column-major, leading dimension lda
@@ -110,6 +113,7 @@ struct SyrkSrc {
     const double* P;
     int64_t ldp;
     int part, ncol1;
+    int pf_mode;     // how the next tile's C lines are pulled towards L2: 0 none, 1 prefetch.global.L2 per thread, 2 TMA bulk prefetch
     __device__ __forceinline__ TileDesc tile(int t) const {
         int r, jrel;
         if (part == 0) {
@@ -216,14 +220,21 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 
     const int64_t coff0 = (wi * 32 + tq * 2);
     const int joff0 = wj * 32 + g4;
-    if (MODE == 1 && first_tile < ntiles) {  // the first tile's C lines: towards L2 now
-        const TileDesc t0 = src.tile(first_tile);
-        const double* c0 = t0.C + coff0 + (int64_t)joff0 * t0.ldc;
+    // pull a tile's C lines (128 rows x 64 columns, read-modify-written by this CTA) towards L2 ahead of use
+    auto prefetch_c = [&](const TileDesc& t) {
+        int mode = 1;
+        if constexpr (MODE == 1) mode = src.pf_mode;
+        if (mode == 1) {
+            const double* c0 = t.C + coff0 + (int64_t)joff0 * t.ldc;
 #pragma unroll
-        for (int mj = 0; mj < 4; ++mj)
+            for (int mj = 0; mj < 4; ++mj)
 #pragma unroll
-            for (int ni = 0; ni < 4; ni += 2) prefetch_l2(c0 + ni * 8 + (int64_t)(mj * 8) * t0.ldc);
-    }
+                for (int ni = 0; ni < 4; ni += 2) prefetch_l2(c0 + ni * 8 + (int64_t)(mj * 8) * t.ldc);
+        } else if (mode == 2) {
+            if (lane < 8) tma_prefetch_l2(t.C + (int64_t)(warp * 8 + lane) * t.ldc, BI * 8);
+        }
+    };
+    if (MODE == 1 && first_tile < ntiles) prefetch_c(src.tile(first_tile));
 
     int g = 0;  // consumed items
 #pragma unroll 1
@@ -242,14 +253,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
                     acc[mj][ni][0] = v.x;
                     acc[mj][ni][1] = v.y;
                 }
-            if (tile + tile_stride < ntiles) {  // next tile's C lines: towards L2 while this tile computes
-                const TileDesc tn = src.tile(tile + tile_stride);
-                const double* cn = tn.C + coff0 + (int64_t)joff0 * tn.ldc;
-#pragma unroll
-                for (int mj = 0; mj < 4; ++mj)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni += 2) prefetch_l2(cn + ni * 8 + (int64_t)(mj * 8) * tn.ldc);
-            }
+            if (tile + tile_stride < ntiles) prefetch_c(src.tile(tile + tile_stride));  // while this tile computes
         } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -315,16 +319,17 @@ __global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) 
     gemm_persistent<0>(src, ntiles, blockIdx.x, gridDim.x, sm);
 }
 
-// Blocks [0, nctas) are persistent tile workers; blocks [nctas, nctas + nres) update the residual
-// r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + (block - nctas) (deterministic two-half sum).
+// Blocks [0, nres) update the residual r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block
+// (deterministic two-half sum); they come FIRST so they are not left waiting for a slot behind the persistent
+// tile workers, blocks [nres, nres + nctas).
 __global__ void __launch_bounds__(256, 2)
-syrk2_kernel(SyrkSrc src, int ntiles, int nctas, const double* __restrict__ yk, double* __restrict__ rvec,
+syrk2_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0) {
     extern __shared__ double sm[];
-    if ((int)blockIdx.x < nctas) {
-        gemm_persistent<1>(src, ntiles, blockIdx.x, nctas, sm);
+    if ((int)blockIdx.x >= nres) {
+        gemm_persistent<1>(src, ntiles, (int)blockIdx.x - nres, nctas, sm);
     } else {
-        const int I = src.row0 + ((int)blockIdx.x - nctas);
+        const int I = src.row0 + (int)blockIdx.x;
         const int tid = threadIdx.x;
         const int row = tid & (NB - 1), half = tid >> 7;
         const double* p = src.P + (int64_t)I * NB + row + (int64_t)(res_col0 + half * 64) * src.ldp;
