@@ -22,7 +22,8 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    extra = os.environ.get("PSOAP_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as fh:
