@@ -53,6 +53,7 @@ int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
 int g_potrf_version = 3;
 int g_pf_mode = 2;
+int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
@@ -70,6 +71,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = atoi(c);
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
+        if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -78,9 +80,10 @@ int set_kernel_attributes() {
 
 // Device scratch of one factorisation: W [Nt x Nt] (Nt = padded total dimension), two panel buffers,
 // L_kk^-1, residual, y, accumulators, info.
+constexpr int MAX_GROUP = 4;  // panels per trailing update (rank 128 * G)
 struct FactorWs {
     double* W;
-    double* P[2];   // two pair buffers, each column-major [Nt, 256] (two adjacent 128-wide panels)
+    double* P[2];   // two group buffers, each column-major [Nt, 128 * MAX_GROUP] (the adjacent panels of a group)
     double* Linv;
     double* rvec;
     double* y;
@@ -92,7 +95,7 @@ struct FactorWs {
 size_t factor_ws_bytes(int64_t Nt) {
     size_t b = 0;
     b += align_up((size_t)Nt * Nt * 8, 256);
-    b += 2 * align_up((size_t)Nt * 2 * NB * 8, 256);
+    b += 2 * align_up((size_t)Nt * MAX_GROUP * NB * 8, 256);
     b += align_up((size_t)NB * NB * 8, 256);
     b += 2 * align_up((size_t)Nt * 8, 256);
     b += align_up(8 * 8, 256);
@@ -105,8 +108,8 @@ void carve_factor_ws(char* base, int64_t Nt, FactorWs* ws, bool with_W) {
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
     ws->Nt = Nt;
     ws->W = with_W ? (double*)take((size_t)Nt * Nt * 8) : nullptr;
-    ws->P[0] = (double*)take((size_t)Nt * 2 * NB * 8);
-    ws->P[1] = (double*)take((size_t)Nt * 2 * NB * 8);
+    ws->P[0] = (double*)take((size_t)Nt * MAX_GROUP * NB * 8);
+    ws->P[1] = (double*)take((size_t)Nt * MAX_GROUP * NB * 8);
     ws->Linv = (double*)take((size_t)NB * NB * 8);
     ws->rvec = (double*)take((size_t)Nt * 8);
     ws->y = (double*)take((size_t)Nt * 8);
@@ -120,19 +123,25 @@ struct Lanes {
     cudaStream_t main;
     cudaStream_t side;   // may be null: no look-ahead
     cudaEvent_t e1, e2;
+    int group = 0;       // panels per trailing update (2 or 4); 0 = choose from the problem size
 };
 
 // Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
 // (T_elim == T_total: plain Cholesky).  The trailing block is left holding the Schur complement.
 //
-// Panels are processed in PAIRS (a, b = a+1): after panel a is factored its update is applied to block column b
-// only (K = 128, 2R tiles); then b is factored and the trailing matrix gets ONE rank-256 update with [P_a | P_b],
-// which halves the read-modify-write traffic and the per-tile overhead of the dominant kernel.
-// Look-ahead: the rank-256 update first covers the next pair's two block columns (part 1); the next pair's
-// head (potrf, trsm, column update, potrf, trsm) then runs on the side stream under the rest of the update.
+// Panels are processed in GROUPS of G (2 or 4): inside a group, before panel g is factored its block column gets
+// ONE update with all the group's earlier panels (left-looking, K = 128 g, 2R tiles); after the last panel the
+// trailing matrix gets ONE rank-128G update with [P_0 | ... | P_{G-1}], which divides the read-modify-write
+// traffic and the per-tile overhead of the dominant kernel by G.
+// Look-ahead: the big update first covers the next group's block columns (part 1); the next group's head
+// (potrf, trsm, column update, ...) then runs on the side stream under the rest of the update.
 int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
                   const int* sentinel, double* result) {
     const int64_t ldp = ws.Nt;
+    // Rank-512 updates (G = 4) are worth their longer panel chain when that chain is hidden anyway (the farm:
+    // measured 4.30 -> 4.37 evals/s on C4) or when the matrix is large (N = 16384: 50.0 -> 49.1 ms); a single
+    // mid-size matrix is faster with G = 2 (N = 9000: 11.2 vs 11.7 ms).
+    const int G = g_group ? g_group : (ln.group ? ln.group : (T_total >= 96 ? 4 : 2));
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
     auto potrf = [&](cudaStream_t s, int kb) {
@@ -150,51 +159,53 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
         trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
     };
-    // update of row tiles [row0, T_total) with k range [kbeg, kend) of pair buffer q; residual with y of panel ykb
+    // update of row tiles [row0, T_total) with k range [kbeg, kend) of group buffer q; the residual blocks (if
+    // ykb >= 0) apply panel ykb, whose columns start at res_col0 in the buffer
     auto syrk = [&](cudaStream_t s, int q, int row0, int kend, int part, int ncol1, int ykb, int res_col0) {
         const int R = T_total - row0;
         SyrkSrc src;
         src.W = W; src.ld = ld; src.row0 = row0; src.kbeg = kbeg_of(q); src.kend = kend;
         src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = ncol1; src.pf_mode = g_pf_mode;
         const int ntiles = syrk_ntiles(R, part, ncol1);
-        const int nres = part == 2 ? 0 : R;
+        const int nres = (part == 2 || ykb < 0) ? 0 : R;
         if (ntiles + nres == 0) return;
         // Under look-ahead the bulk update (part 2) gives up persistence: one tile per CTA, so SM slots free up
-        // continuously and the high-priority side stream (next pair's potrf/trsm) is scheduled into them.
+        // continuously and the high-priority side stream (next group's potrf/trsm) is scheduled into them.
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
-        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)ykb * NB, ws.rvec, res_col0);
+        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
+                                                          ws.rvec, res_col0);
         ++g_launches;
     };
-    const int npairs = (T_elim + 1) / 2;
-    // everything of pair q that precedes its big update
+    const int ngroups = (T_elim + G - 1) / G;
+    auto group_size = [&](int q) { return std::min(G, T_elim - q * G); };
+    // everything of group q that precedes its big update: for each panel g: (column update with the group's
+    // earlier panels, which also carries the residual update of panel g-1), potrf, trsm
     auto head = [&](cudaStream_t s, int q) -> int {
-        const int a = 2 * q, b = a + 1;
-        potrf(s, a); LAUNCH_CHECK();
-        if (T_total - a - 1 <= 0) return PSOAP_OK;
-        trsm(s, a, q, 0); LAUNCH_CHECK();
-        if (b >= T_elim) return PSOAP_OK;
-        syrk(s, q, a + 1, NB, 1, 2, a, 0);          // block column b only (+ residual of panel a)
-        potrf(s, b); LAUNCH_CHECK();
-        if (T_total - b - 1 > 0) { trsm(s, b, q, NB); LAUNCH_CHECK(); }
+        const int a = q * G, n = group_size(q);
+        for (int g = 0; g < n; ++g) {
+            const int kb = a + g;
+            if (g > 0) syrk(s, q, kb, g * NB, 1, 2, kb - 1, (g - 1) * NB);   // block column kb, K = 128 g
+            potrf(s, kb); LAUNCH_CHECK();
+            if (T_total - kb - 1 > 0) { trsm(s, kb, q, g * NB); LAUNCH_CHECK(); }
+        }
         return PSOAP_OK;
     };
-    // the big update of pair q: rank 256 when the pair is complete, rank 128 for a trailing single panel
+    // the big update of group q with all its panels (the residual blocks apply its last panel)
     auto update = [&](cudaStream_t s, int q, int part, int ncol1) {
-        const int a = 2 * q, b = a + 1;
-        if (b < T_elim) syrk(s, q, b + 1, 2 * NB, part, ncol1, b, NB);
-        else syrk(s, q, a + 1, NB, part, ncol1, a, 0);
+        const int a = q * G, n = group_size(q);
+        syrk(s, q, a + n, n * NB, part, ncol1, a + n - 1, (n - 1) * NB);
     };
     int rc = head(ln.main, 0);
     if (rc) return rc;
-    for (int q = 0; q < npairs; ++q) {
-        const bool next = q + 1 < npairs;
+    for (int q = 0; q < ngroups; ++q) {
+        const bool next = q + 1 < ngroups;
         if (!next || ln.side == nullptr) {
             update(ln.main, q, 0, 2);
             if (next) { rc = head(ln.main, q + 1); if (rc) return rc; }
             continue;
         }
-        const int ncol1 = (2 * (q + 1) + 1 < T_elim) ? 4 : 2;   // block columns the next pair's head touches
+        const int ncol1 = 2 * group_size(q + 1);   // block columns the next group's head touches
         update(ln.main, q, 1, ncol1);
         CUDA_TRY(cudaEventRecord(ln.e1, ln.main));
         CUDA_TRY(cudaStreamWaitEvent(ln.side, ln.e1, 0));
@@ -635,6 +646,7 @@ int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const ps
             ln.main = sb;
             ln.side = lookahead ? f->side_streams[b] : nullptr;
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
+            ln.group = lookahead ? 0 : 4;
             rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + it, f->results + 4 * it);
             if (rc) break;
         }

@@ -101,10 +101,10 @@ struct TrsmSrc {
 };
 
 // syrk tiles: W[I, J] -= P_I P_J^T over the row tiles I = row0 + r, r in [0, R), with P the panel buffer
-// [Nt, 256] (two adjacent 128-wide panels; k range [kbeg, kend), kend = 128 or 256).  Row r owns the 128 x 64
+// [Nt, 128 G] (the G adjacent 128-wide panels of a group; k range [kbeg, kend), kend a multiple of 128).  Row r owns the 128 x 64
 // tiles jrel in [0, 2r+2), J64 = 2 row0 + jrel.
 //   part 0: all of them
-//   part 1: jrel < ncol1 (ncol1 = 2 or 4: the next one or two panels' block columns, for look-ahead)
+//   part 1: jrel < ncol1 (ncol1 = 2 per panel of the next group: its block columns, for look-ahead)
 //   part 2: jrel >= ncol1
 struct SyrkSrc {
     double* W;
@@ -122,15 +122,16 @@ struct SyrkSrc {
             while (r * (r + 1) > t) --r;
             jrel = t - r * (r + 1);
         } else if (part == 1) {
-            if (ncol1 == 2) {
-                r = t >> 1;
-                jrel = t & 1;
-            } else if (t < 2) {
-                r = 0;
-                jrel = t;
+            // rows r < h = ncol1/2 are still triangular (2r+2 tiles), rows r >= h have ncol1 tiles each
+            const int h = ncol1 >> 1, tri = h * (h + 1);
+            if (t < tri) {
+                r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while ((r + 1) * (r + 2) <= t) ++r;
+                while (r * (r + 1) > t) --r;
+                jrel = t - r * (r + 1);
             } else {
-                r = 1 + ((t - 2) >> 2);
-                jrel = (t - 2) & 3;
+                r = h + (t - tri) / ncol1;
+                jrel = (t - tri) % ncol1;
             }
         } else {
             int v = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
@@ -158,7 +159,7 @@ struct SyrkSrc {
 __host__ __device__ inline int syrk_ntiles(int R, int part, int ncol1) {
     const int h = ncol1 >> 1;
     if (part == 0) return R * (R + 1);
-    if (part == 1) return ncol1 == 2 ? 2 * R : (R >= 1 ? 2 + 4 * (R - 1) : 0);
+    if (part == 1) return R <= h ? R * (R + 1) : h * (h + 1) + (R - h) * ncol1;
     return R > h ? (R - h) * (R - h + 1) : 0;
 }
 
