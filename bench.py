@@ -229,14 +229,15 @@ def main():
         _lib.check(lib.psoap_fp64_peak_tflops(ctypes.byref(peak)))
         avg_ms, fl = ctypes.c_double(), ctypes.c_double()
         m_syrk = 4096 if args.workload in ("C1", "C4") else 8192
-        _lib.check(lib.psoap_bench_syrk(m_syrk, 256, 20, ctypes.byref(avg_ms), ctypes.byref(fl)))
+        k_syrk = 512 if args.workload in ("C4", "C5") else 256   # the rank the orchestration uses for this workload
+        _lib.check(lib.psoap_bench_syrk(m_syrk, k_syrk, 20, ctypes.byref(avg_ms), ctypes.byref(fl)))
         achieved = fl.value / (avg_ms.value * 1e-3) * 1e-12
         step_tflops = flops_total * value * 1e-12 / world
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "syrk_traffic.json")
         if os.path.exists(tfile):
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch_m%d" % m_syrk)
-        roofline = {"bound": "tensor", "kernel": "syrk2_kernel (DMMA.8x8x4 rank-256 trailing update of an m=%d lower triangle)" % m_syrk,
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch_m%d_k%d" % (m_syrk, k_syrk))
+        roofline = {"bound": "tensor", "kernel": "syrk2_kernel (DMMA.8x8x4 rank-%d trailing update of an m=%d lower triangle)" % (k_syrk, m_syrk),
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
                     "peak_source": "live DMMA.8x8x4 register-resident loop on all SMs (psoap_fp64_peak_tflops); "
