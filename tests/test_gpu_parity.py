@@ -141,6 +141,20 @@ def test_lnlike_vs_oracle(model, n_epochs, n_pix, mask_frac, oracle, torch_cuda)
     assert got_dev == got
 
 
+@pytest.mark.parametrize("n_pix", [127, 128, 129, 255, 256, 257, 383, 384, 385, 511, 513, 640, 897])
+def test_lnlike_tile_boundaries(n_pix, oracle, torch_cuda):
+    """Sizes around the 128-row tile / 2- and 4-panel group boundaries (front padding, partial groups)."""
+    from psoap_b200 import covariance, synthetic
+    ch = synthetic.make_chunk("SB2", 1, n_pix, seed=n_pix, dv_pix=1.4)
+    p = synthetic.default_params("SB2")
+    vel = oracle.get_velocities("SB2", p[:7], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    V11 = np.empty((ch["N"], ch["N"]))
+    ref = oracle.lnlike_f_g(V11, lwls[0], lwls[1], ch["fl"], ch["sigma"], *p[7:])
+    got = covariance.lnlike_f_g(None, lwls[0], lwls[1], ch["fl"], ch["sigma"], *p[7:])
+    assert rel_close(got, ref, LNLIKE_RTOL), (n_pix, got, ref)
+
+
 def test_lnlike_materialize_v11(oracle, torch_cuda):
     from psoap_b200 import covariance, synthetic
     ch = synthetic.make_chunk("SB2", 4, 50, seed=3)
