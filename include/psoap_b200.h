@@ -150,6 +150,10 @@ int psoap_fp64_peak_tflops(double *tflops_out);
  * rank-K update (K = 128 or 256) of an m x m lower triangle, CUDA events on the launching stream.
  * flops_per_launch is the algorithmic count K m (m + 128). Synchronous. */
 int psoap_bench_syrk(int64_t m, int K, int reps, double *avg_ms_out, double *flops_per_launch_out);
+/* Host-side replay of the trailing-update tile enumeration (csrc/gemm.cuh SyrkSrc::decode; no device work): the
+ * (row tile r, 64-column tile jrel) of every tile of a launch over R row tiles for part 0 (all), 1 (first ncol1
+ * column tiles of every row) or 2 (the rest).  Returns the tile count, -1 if cap is too small. */
+int psoap_debug_syrk_tiles(int R, int part, int ncol1, int *rows_out, int *cols_out, int cap);
 /* Number of kernels launched by this library since load (for bench.py's gpu_launches). */
 int64_t psoap_launch_count(void);
 

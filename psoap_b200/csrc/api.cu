@@ -739,6 +739,17 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     return PSOAP_OK;
 }
 
+// Host-side replay of the trailing-update tile enumeration (no device work): writes (row, column-tile) of every
+// tile of a launch over R row tiles; returns the tile count, or -1 when `cap` is too small.
+int psoap_debug_syrk_tiles(int R, int part, int ncol1, int* rows_out, int* cols_out, int cap) {
+    SyrkSrc src{};
+    src.part = part; src.ncol1 = ncol1;
+    const int n = syrk_ntiles(R, part, ncol1);
+    if (n > cap) return -1;
+    for (int t = 0; t < n; ++t) src.decode(t, rows_out[t], cols_out[t]);
+    return n;
+}
+
 int psoap_fp64_peak_tflops(double* tflops_out) {
     if (!tflops_out) return fail(PSOAP_ERR_ARG, "psoap_fp64_peak_tflops: null");
     int dev = 0, sms = 0;

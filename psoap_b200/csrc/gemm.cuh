@@ -19,6 +19,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifdef __CUDA_ARCH__
+#define PSOAP_FSQRT(x) __fsqrt_rn(x)   // FP32: the FP64 pipe belongs to DMMA
+#else
+#include <cmath>
+#define PSOAP_FSQRT(x) sqrtf(x)
+#endif
+
 namespace psoap {
 
 constexpr int BI = 128, BJ = 64, BK = 16, STAGES = 4;
@@ -114,10 +121,10 @@ struct SyrkSrc {
     int64_t ldp;
     int part, ncol1;
     int pf_mode;     // how the next tile's C lines are pulled towards L2: 0 none, 1 prefetch.global.L2 per thread, 2 TMA bulk prefetch
-    __device__ __forceinline__ TileDesc tile(int t) const {
-        int r, jrel;
+    // tile index -> (row r, 64-column tile jrel); host-callable so the CPU tests can check the coverage
+    __host__ __device__ __forceinline__ void decode(int t, int& r, int& jrel) const {
         if (part == 0) {
-            r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // FP32: the FP64 pipe belongs to DMMA
+            r = (int)((PSOAP_FSQRT(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
             while ((r + 1) * (r + 2) <= t) ++r;
             while (r * (r + 1) > t) --r;
             jrel = t - r * (r + 1);
@@ -125,7 +132,7 @@ struct SyrkSrc {
             // rows r < h = ncol1/2 are still triangular (2r+2 tiles), rows r >= h have ncol1 tiles each
             const int h = ncol1 >> 1, tri = h * (h + 1);
             if (t < tri) {
-                r = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                r = (int)((PSOAP_FSQRT(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
                 while ((r + 1) * (r + 2) <= t) ++r;
                 while (r * (r + 1) > t) --r;
                 jrel = t - r * (r + 1);
@@ -134,12 +141,16 @@ struct SyrkSrc {
                 jrel = (t - tri) % ncol1;
             }
         } else {
-            int v = (int)((__fsqrt_rn(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
+            int v = (int)((PSOAP_FSQRT(4.0f * (float)t + 1.0f) + 1.0f) * 0.5f);
             while ((v + 1) * v <= t) ++v;
             while (v * (v - 1) > t) --v;
             jrel = ncol1 + t - v * (v - 1);
             r = v + (ncol1 >> 1) - 1;
         }
+    }
+    __device__ __forceinline__ TileDesc tile(int t) const {
+        int r, jrel;
+        decode(t, r, jrel);
         const int I = row0 + r;
         const int J64 = 2 * row0 + jrel;
         TileDesc d;

@@ -68,3 +68,26 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f"{f} reaches into oracle/"
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 5, 8, 47, 256])
+def test_trailing_update_tiles_cover_the_lower_triangle_exactly_once(lib, R):
+    """Tile enumeration of the dominant kernel (host replay of SyrkSrc::decode): part 0 covers every 128x64 tile
+    of the lower triangle once; for look-ahead, parts 1 and 2 split it without overlap for every group size."""
+    import ctypes
+    full = {(r, j) for r in range(R) for j in range(2 * r + 2)}
+    cap = R * (R + 1) + 16
+    rows, cols = (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+
+    def tiles(part, ncol1):
+        n = lib.psoap_debug_syrk_tiles(R, part, ncol1, rows, cols, cap)
+        assert n >= 0
+        out = [(rows[i], cols[i]) for i in range(n)]
+        assert len(set(out)) == n, "a tile is visited twice"
+        return set(out)
+
+    assert tiles(0, 2) == full
+    for ncol1 in (2, 4, 6, 8):
+        p1, p2 = tiles(1, ncol1), tiles(2, ncol1)
+        assert p1 == {(r, j) for (r, j) in full if j < ncol1}
+        assert p2 == {(r, j) for (r, j) in full if j >= ncol1}
