@@ -158,7 +158,6 @@ def main():
     p = synthetic.default_params(model)
     farm = ChunkFarm(model, chunks, nbranch=args.nbranch, rank=rank, world_size=world)
     flops_total = float(sum(c["N"] ** 3 / 3.0 + 2.0 * c["N"] ** 2 for c in chunks))
-    rng = np.random.default_rng(0)
 
     def proposal(k):
         # a fresh proposal every step (tiny random-walk around the truth), identical on every rank

@@ -123,3 +123,21 @@ def test_mh_sampler_recovers_a_gaussian():
     s2 = MHSampler(np.diag((1.2 * sig) ** 2), 2, lnp, seed=3)
     s2.run_mcmc(mean, 100)
     assert np.array_equal(s2.flatchain, s.flatchain[:100])  # same seed, same chain: the replicated-rank contract
+
+
+def test_load_chunk_npz_matches_reference_chunk_semantics(tmp_path):
+    """sample.load_chunk: the reference's chunk datasets (data.py:149-197) -> the masked, flattened attributes a
+    Chunk exposes after apply_mask() (data.py:120-147), honouring the epoch limit."""
+    from psoap_b200 import sample
+    rng = np.random.default_rng(4)
+    wl = np.tile(np.linspace(5000.0, 5010.0, 30), (6, 1))
+    fl, sigma = rng.normal(1.0, 0.01, wl.shape), np.full(wl.shape, 0.01)
+    date = np.tile(np.arange(6.0)[:, None], (1, 30))
+    mask = rng.uniform(size=wl.shape) > 0.1
+    f = str(tmp_path / "chunk_22_5000_5010.npz")
+    np.savez(f, wl=wl, fl=fl, sigma=sigma, date=date, mask=mask)
+    ch = sample.load_chunk(f, limit=4)
+    m = mask[:4]
+    assert np.array_equal(ch["lwl"], np.log(wl[:4])[m]) and np.array_equal(ch["fl"], fl[:4][m])
+    assert np.array_equal(ch["date1D"], np.arange(4.0)) and ch["mask"].shape == (4, 30)
+    assert len(ch["sigma"]) == m.sum()
