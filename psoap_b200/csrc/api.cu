@@ -1,4 +1,5 @@
 // api.cu — host orchestration and the C ABI (include/psoap_b200.h) of the sm_100a PSOAP likelihood path.
+#include <cudaTypedefs.h>
 #include <math_constants.h>
 
 #include <algorithm>
@@ -46,6 +47,23 @@ int fail(int code, const std::string& msg) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
 
+// ---- 2-D tensor maps for the TMA operand loads (driver entry point fetched at run time: no -lcuda) ----------
+PFN_cuTensorMapEncodeTiled g_encode_tiled = nullptr;
+int g_use_tmap = 1;  // PSOAP_TMAP=0 falls back to per-column bulk copies
+
+// column-major FP64 matrix [rows, cols] with leading dimension ld; box = {box_rows, 16 columns}
+int make_tensor_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    const cuuint64_t gdim[2] = {rows, cols};
+    const cuuint64_t gstride[1] = {ld * 8};
+    const cuuint32_t box[2] = {box_rows, (cuuint32_t)BK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PSOAP_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return PSOAP_OK;
+}
+
 std::once_flag g_attr_once;
 int g_attr_status = 0;
 int g_num_sms = 148;
@@ -61,6 +79,10 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int dev = 0;
@@ -71,6 +93,17 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = atoi(c);
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
+        if (const char* c = getenv("PSOAP_TMAP")) g_use_tmap = atoi(c);
+        if (e == cudaSuccess && g_use_tmap) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                qres == cudaDriverEntryPointSuccess && fn)
+                g_encode_tiled = (PFN_cuTensorMapEncodeTiled)fn;
+            else
+                g_use_tmap = 0;
+            cudaGetLastError();
+        }
         if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
     });
     if (g_attr_status != 0)
@@ -138,6 +171,18 @@ struct Lanes {
 int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
                   const int* sentinel, double* result) {
     const int64_t ldp = ws.Nt;
+    CUtensorMap mapW, mapLinv, mapPa[2], mapPb[2];
+    const bool tmap = g_use_tmap != 0;
+    if (tmap) {
+        const uint64_t Nt = (uint64_t)T_total * NB;
+        int rcm = make_tensor_map(&mapW, W, Nt, Nt, (uint64_t)ld, SA);
+        if (!rcm) rcm = make_tensor_map(&mapLinv, ws.Linv, NB, NB, NB, SB);
+        for (int q = 0; q < 2 && !rcm; ++q) {
+            rcm = make_tensor_map(&mapPa[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SA);
+            if (!rcm) rcm = make_tensor_map(&mapPb[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SB);
+        }
+        if (rcm) return rcm;
+    }
     // Rank-512 updates (G = 4) are worth their longer panel chain when that chain is hidden anyway (the farm:
     // measured 4.30 -> 4.37 evals/s on C4) or when the matrix is large (N = 16384: 50.0 -> 49.1 ms); a single
     // mid-size matrix is faster with G = 2 (N = 9000: 11.2 vs 11.7 ms).
@@ -157,7 +202,8 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         TrsmSrc src;
         src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
         src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
-        trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
+        if (tmap) trsm3_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R, mapW, mapLinv);
+        else trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
     };
     // update of row tiles [row0, T_total) with k range [kbeg, kend) of group buffer q; the residual blocks (if
     // ykb >= 0) apply panel ykb, whose columns start at res_col0 in the buffer
@@ -173,8 +219,12 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         // continuously and the high-priority side stream (next group's potrf/trsm) is scheduled into them.
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
-        syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
-                                                          ws.rvec, res_col0);
+        if (tmap)
+            syrk3_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
+                                                              ws.rvec, res_col0, mapPa[q & 1], mapPb[q & 1]);
+        else
+            syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
+                                                              ws.rvec, res_col0);
         ++g_launches;
     };
     const int ngroups = (T_elim + G - 1) / G;
@@ -725,9 +775,20 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     src.W = W; src.ld = m; src.row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
     src.pf_mode = g_pf_mode;
     const int nctas = persistent_ctas(ntiles);
-    for (int w = 0; w < 2; ++w) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0); ++g_launches; }
+    CUtensorMap mapPa, mapPb;
+    if (g_use_tmap) {
+        rc = make_tensor_map(&mapPa, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SA);
+        if (!rc) rc = make_tensor_map(&mapPb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SB);
+        if (rc) return rc;
+    }
+    auto launch = [&]() {
+        if (g_use_tmap) syrk3_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
+        else syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0);
+        ++g_launches;
+    };
+    for (int w = 0; w < 2; ++w) launch();
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; ++i) { syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0); ++g_launches; }
+    for (int i = 0; i < reps; ++i) launch();
     cudaEventRecord(e1, st);
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;

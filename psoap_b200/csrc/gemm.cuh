@@ -17,6 +17,7 @@
 //   mma M <-> j, mma N <-> i, so each thread owns two consecutive rows i of a column j: double2 epilogue on the
 //   column-major output.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 
 #ifdef __CUDA_ARCH__
@@ -66,6 +67,16 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG): box {rows, 16 k-columns} of a column-major matrix lands as
+// [16][rows] in shared memory; with a box of 132 (68) rows that IS the padded, bank-conflict-free stage layout, so a
+// whole operand stage is ONE instruction.  c0 = row coordinate, c1 = column coordinate.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void tma_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
@@ -79,6 +90,8 @@ struct TileDesc {
     int kbeg, KT;      // k range [kbeg, kbeg + 16 KT), KT >= 1
     double* C;         // [128, 64] column-major output tile
     int64_t ldc;
+    int rowA, rowB;    // tensor-map path: first row of the operands in their maps
+    int colA0, colB0;  //                  column of k = 0 in their maps
 };
 
 // trsm tiles: rows below panel kb.  tile t -> row tile I = kb+1 + t/2, column half jh = t%2:
@@ -103,6 +116,8 @@ struct TrsmSrc {
         d.KT = (kend - kb0) / BK;
         d.C = P + (int64_t)I * NB + (int64_t)jh * BJ * ldp;
         d.ldc = ldp;
+        d.rowA = I * NB; d.colA0 = kb * NB;   // map A: W
+        d.rowB = jh * BJ; d.colB0 = 0;        // map B: Linv
         return d;
     }
 };
@@ -162,6 +177,7 @@ struct SyrkSrc {
         d.KT = (kend - kbeg) / BK;
         d.C = W + (int64_t)I * NB + (int64_t)J64 * BJ * ld;
         d.ldc = ld;
+        d.rowA = I * NB; d.rowB = J64 * BJ; d.colA0 = d.colB0 = 0;   // both operands: the group buffer's map
         return d;
     }
 };
@@ -178,9 +194,11 @@ __device__ __forceinline__ double flip_sign(double x) {  // integer pipe, keeps 
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
 }
 
-template <int MODE, class Src>  // MODE 0: C = acc, 1: C -= acc
-__device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride,
-                                                double* sm) {
+// MODE 0: C = acc, 1: C -= acc.  TMAP: operands staged by 2-D tensor-map TMA (one elected thread, two instructions
+// per stage) instead of per-column bulk copies spread over the warps.
+template <int MODE, bool TMAP, class Src>
+__device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride, double* sm,
+                                                const CUtensorMap* mapA = nullptr, const CUtensorMap* mapB = nullptr) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g4 = lane >> 2, tq = lane & 3;
@@ -190,7 +208,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], GEMM_WARPS);
+            mbar_init(&full[s], TMAP ? 1 : GEMM_WARPS);
             mbar_init(&empty[s], GEMM_WARPS);
         }
         mbar_fence_init();
@@ -206,7 +224,17 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     if (p_valid) pd = src.tile(p_tile);
     auto produce = [&]() {
         const int s = produced % STAGES;
-        if (lane == 0) {
+        if (TMAP) {
+            if (tid == 0) {
+                if (produced >= STAGES) mbar_wait(&empty[s], ((produced / STAGES) - 1) & 1);
+                double* sA = sm + s * STAGE_DOUBLES;
+                double* sB = sA + BK * SA;
+                const int k0 = pd.kbeg + p_kt * BK;
+                mbar_arrive_expect_tx(&full[s], STAGE_DOUBLES * 8);
+                tma_load_2d(sA, mapA, pd.rowA, pd.colA0 + k0, &full[s]);
+                tma_load_2d(sB, mapB, pd.rowB, pd.colB0 + k0, &full[s]);
+            }
+        } else if (lane == 0) {
             if (produced >= STAGES) mbar_wait(&empty[s], ((produced / STAGES) - 1) & 1);
             double* sA = sm + s * STAGE_DOUBLES;
             double* sB = sA + BK * SA;
@@ -331,8 +359,28 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 
 // Persistent launch geometry: `nctas` CTAs walk the tiles round-robin.
 __global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) {
-    extern __shared__ double sm[];
-    gemm_persistent<0>(src, ntiles, blockIdx.x, gridDim.x, sm);
+    extern __shared__ __align__(128) double sm[];
+    gemm_persistent<0, false>(src, ntiles, blockIdx.x, gridDim.x, sm);
+}
+__global__ void __launch_bounds__(256, 2)
+trsm3_kernel(TrsmSrc src, int ntiles, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapLinv) {
+    extern __shared__ __align__(128) double sm[];
+    gemm_persistent<0, true>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
+}
+
+// residual block: r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block (deterministic two-half sum)
+__device__ __forceinline__ void syrk_residual_block(const SyrkSrc& src, const double* __restrict__ yk,
+                                                    double* __restrict__ rvec, int res_col0, double* sm) {
+    const int I = src.row0 + (int)blockIdx.x;
+    const int tid = threadIdx.x;
+    const int row = tid & (NB - 1), half = tid >> 7;
+    const double* p = src.P + (int64_t)I * NB + row + (int64_t)(res_col0 + half * 64) * src.ldp;
+    double s = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) s = fma(p[(int64_t)c * src.ldp], yk[half * 64 + c], s);
+    sm[tid] = s;
+    __syncthreads();
+    if (half == 0) rvec[I * NB + row] -= (sm[row] + sm[NB + row]);
 }
 
 // Blocks [0, nres) update the residual r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block
@@ -341,21 +389,25 @@ __global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) 
 __global__ void __launch_bounds__(256, 2)
 syrk2_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
     if ((int)blockIdx.x >= nres) {
-        gemm_persistent<1>(src, ntiles, (int)blockIdx.x - nres, nctas, sm);
+        gemm_persistent<1, false>(src, ntiles, (int)blockIdx.x - nres, nctas, sm);
     } else {
-        const int I = src.row0 + (int)blockIdx.x;
-        const int tid = threadIdx.x;
-        const int row = tid & (NB - 1), half = tid >> 7;
-        const double* p = src.P + (int64_t)I * NB + row + (int64_t)(res_col0 + half * 64) * src.ldp;
-        double s = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) s = fma(p[(int64_t)c * src.ldp], yk[half * 64 + c], s);
-        sm[tid] = s;
-        __syncthreads();
-        if (half == 0) rvec[I * NB + row] -= (sm[row] + sm[NB + row]);
+        syrk_residual_block(src, yk, rvec, res_col0, sm);
     }
 }
+
+__global__ void __launch_bounds__(256, 2)
+syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
+             int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb) {
+    extern __shared__ __align__(128) double sm[];
+    if ((int)blockIdx.x >= nres) {
+        // same buffer, two boxes: 132 rows for the 128-row operand, 68 rows for the 64-row one
+        gemm_persistent<1, true>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
+    } else {
+        syrk_residual_block(src, yk, rvec, res_col0, sm);
+    }
+}
+
 
 }  // namespace psoap
