@@ -236,7 +236,7 @@ def main():
         tfile = os.path.join(ROOT, "profiles", "syrk_traffic.json")
         if os.path.exists(tfile):
             traffic = json.load(open(tfile)).get("dram_bytes_per_launch_m%d_k%d" % (m_syrk, k_syrk))
-        roofline = {"bound": "tensor", "kernel": "syrk2_kernel (DMMA.8x8x4 rank-%d trailing update of an m=%d lower triangle)" % (k_syrk, m_syrk),
+        roofline = {"bound": "tensor", "kernel": "syrk3_kernel (tensor-map TMA + DMMA.8x8x4 rank-%d trailing update of an m=%d lower triangle)" % (k_syrk, m_syrk),
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
                     "peak_source": "live DMMA.8x8x4 register-resident loop on all SMs (psoap_fp64_peak_tflops); "

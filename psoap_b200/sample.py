@@ -108,17 +108,18 @@ class MHSampler:
 # --------------------------------------------------------------------------------------------------
 def load_chunk(fname, limit=100):
     """-> dict(lwl, fl, sigma, mask, date1D) after apply_mask() (psoap/data.py:120-147), first `limit` epochs."""
+    from .data import Chunk
     if fname.endswith(".npz"):
         with np.load(fname) as f:
-            arr = {k: f[k][:limit] for k in ("wl", "fl", "sigma", "date", "mask")}
+            arr = {k: f[k][:limit] for k in Chunk.DATASETS}
     else:
         import h5py  # optional dependency
         with h5py.File(fname, "r") as f:
-            arr = {k: f[k][:limit] for k in ("wl", "fl", "sigma", "date", "mask")}
-    mask = np.array(arr["mask"], dtype=bool)
-    wl = arr["wl"].astype(np.float64)
-    return dict(lwl=np.log(wl)[mask], fl=arr["fl"].astype(np.float64)[mask],
-                sigma=arr["sigma"].astype(np.float64)[mask], mask=mask, date1D=arr["date"].astype(np.float64)[:, 0])
+            arr = {k: f[k][:limit] for k in Chunk.DATASETS}
+    ch = Chunk(arr["wl"].astype(np.float64), arr["fl"].astype(np.float64), arr["sigma"].astype(np.float64),
+               arr["date"].astype(np.float64), np.array(arr["mask"], dtype=bool))
+    ch.apply_mask()
+    return ch.as_farm_chunk()
 
 
 def make_lnprob(farm, model, fix_params, pars, prior=None):

@@ -141,3 +141,55 @@ def test_load_chunk_npz_matches_reference_chunk_semantics(tmp_path):
     assert np.array_equal(ch["lwl"], np.log(wl[:4])[m]) and np.array_equal(ch["fl"], fl[:4][m])
     assert np.array_equal(ch["date1D"], np.arange(4.0)) and ch["mask"].shape == (4, 30)
     assert len(ch["sigma"]) == m.sum()
+
+
+def test_chunk_container_roundtrip(tmp_path):
+    """Chunk mirrors psoap/data.py:120-197: attributes, apply_mask flattening, file naming, limit on open."""
+    from psoap_b200 import data
+    rng = np.random.default_rng(5)
+    n_epochs, n_pix = 6, 9
+    wl = 5000.0 * np.exp(np.arange(n_pix) * 2.8 / 2.99792458e5)[None, :] * np.ones((n_epochs, 1))
+    date = np.sort(rng.uniform(0, 60, n_epochs))[:, None] * np.ones((1, n_pix))
+    mask = rng.uniform(size=wl.shape) > 0.2
+    ch = data.Chunk(wl, 1 + 0.01 * rng.normal(size=wl.shape), np.full(wl.shape, 0.04), date, mask)
+    assert (ch.n_epochs, ch.n_pix) == (n_epochs, n_pix) and np.array_equal(ch.date1D, date[:, 0])
+    fname = ch.save(22, 5160.2, 5190.7, prefix=str(tmp_path) + "/", fmt="npz")
+    assert fname.endswith("chunk_22_5160_5191.npz")           # constants.py:39 format
+    back = data.Chunk.open(22, 5160.2, 5190.7, limit=4, prefix=str(tmp_path) + "/")
+    assert back.wl.shape == (4, n_pix) and back.wl.dtype == np.float64 and back.mask.dtype == bool
+    back.apply_mask()
+    assert back.N == int(mask[:4].sum())
+    assert np.array_equal(back.lwl, np.log(wl[:4])[mask[:4]])
+    fc = back.as_farm_chunk()
+    assert set(fc) == {"lwl", "fl", "sigma", "mask", "date1D"} and len(fc["date1D"]) == 4
+    assert np.allclose(data.redshift(np.array([5000.0]), 30.0), 5000.0 * np.sqrt((2.99792458e5 + 30) / (2.99792458e5 - 30)))
+
+
+def test_chunks_dat_table(tmp_path):
+    from psoap_b200 import data
+    rows = [(22, 5160.25, 5190.5), (23, 5200.0, 5230.0)]
+    f = str(tmp_path / "chunks.dat")
+    data.write_chunks_dat(rows, f)
+    assert open(f).readline().split() == ["order", "wl0", "wl1"]
+    assert data.read_chunks_dat(f) == rows
+    (tmp_path / "bad.dat").write_text("a b c\n1 2 3\n")
+    with pytest.raises(ValueError):
+        data.read_chunks_dat(str(tmp_path / "bad.dat"))
+
+
+def test_chain_diagnostics():
+    """utils.get_labels / gelman_rubin / estimate_covariance (psoap/utils.py:87-201)."""
+    from psoap_b200 import utils
+    assert utils.get_labels("SB1", ["gamma", "e"]) == [r"$K$", r"$\omega$", r"$P$", r"$T_0$", r"$a_f$", r"$l_f$"]
+    assert len(utils.get_labels("ST3", [])) == len(utils.registered_params["ST3"])
+    rng = np.random.default_rng(1)
+    good = [rng.normal(size=(400, 2)) for _ in range(3)]
+    mean, std, rhat = utils.gelman_rubin(good)
+    assert np.all(rhat < 1.05) and np.allclose(std, 1.0, atol=0.1) and np.allclose(mean, 0.0, atol=0.15)
+    bad = [good[0], good[1] + np.array([3.0, 0.0])]
+    assert utils.gelman_rubin(bad)[2][0] > 1.1 and utils.gelman_rubin(bad)[2][1] < 1.05
+    with pytest.raises(AssertionError):
+        utils.gelman_rubin([good[0][:399]])
+    fc = rng.normal(size=(2000, 3)) * np.array([1.0, 2.0, 0.5])
+    oj = utils.estimate_covariance(fc)
+    assert np.allclose(oj, 2.38 ** 2 / 3 * np.cov(fc, rowvar=0))
