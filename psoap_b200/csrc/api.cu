@@ -77,6 +77,7 @@ int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF5_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -193,6 +194,9 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         if (g_potrf_version == 1)
             potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
                                                          ws.info, sentinel, kb == T_elim - 1, result);
+        else if (g_potrf_version == 5)   // blocked variant (experimental, same speed today)
+            potrf_diag5_kernel<<<1, 256, POTRF5_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
+                                                           ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
         else
             potrf_diag3_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
                                                           ws.acc, ws.info, sentinel, kb == T_elim - 1, result);

@@ -25,10 +25,43 @@ __device__ __forceinline__ void gp_coeffs(const GpParams& gp, int c, double& amp
     p2 = __ddiv_rn(-0.5 * C_KMS2, __dmul_rn(l, l));
 }
 
+// exp(x) for x <= 0 without a branch (the squared-exponential argument is never positive).  libdevice's exp takes a
+// slow path below -708 — which is where most covariance entries live — and its branches keep the compiler from
+// interleaving the independent evaluations of an unrolled fill loop.  Cody-Waite reduction x = n ln2 + r,
+// |r| <= ln2/2, degree-12 Taylor polynomial (truncation 1.7e-16), result scaled by 2^n in two steps so that the
+// subnormal range rounds once.  Maximum relative error 3.2e-16 against glibc over [-745, 0] (2e7 samples, host copy
+// of this code); exactly 0 below -745.2 and NaN for NaN, like exp.
+__device__ __forceinline__ double exp_neg(double x) {
+    x = (x < -750.0) ? -750.0 : x;
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the integer n lands in the low word of t
+    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const double n = t - SHIFT;
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 479001600.0;
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(t);
+    const int n1 = ni >> 1, n2 = ni - n1;
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    return (p * s1) * s2;
+}
+
 // One covariance term amp2 * exp((p2 * r) * r), r = zj - zi (matrix_functions.pyx:47-49).
 __device__ __forceinline__ double se_term(double amp2, double p2, double zi, double zj) {
     double r = __dsub_rn(zj, zi);
-    return __dmul_rn(amp2, exp(__dmul_rn(__dmul_rn(p2, r), r)));
+    return __dmul_rn(amp2, exp_neg(__dmul_rn(__dmul_rn(p2, r), r)));
 }
 
 // Where the ln-wavelength of component c at data index i comes from: either per-component vectors

@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): covariance entries 1e-12 relative (+1e-30
 exp's denormal range) on bit-identical ln-wavelength inputs; lnlike 1e-10 relative.
 """
 import ctypes
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -432,3 +434,20 @@ def test_farm_many_proposals(oracle, torch_cuda):
         else:
             assert rel_close(got[k], ref, LNLIKE_RTOL) and rel_close(per[k], ref_vec, LNLIKE_RTOL), (k, got[k], ref)
     farm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"PSOAP_TMAP": "0"}, {"PSOAP_POTRF": "5"}, {"PSOAP_POTRF": "1", "PSOAP_GROUP": "2"}],
+                         ids=["per-column-tma", "blocked-potrf", "first-potrf"])
+def test_alternative_kernel_paths(env, torch_cuda):
+    """The library's environment switches select alternative kernels for the same contract (the per-column bulk-copy
+    GEMM staging, the blocked diagonal factorisation, the first diagonal kernel).  They are read once at load time,
+    so the parity tests are re-run in a child process for each."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child_env = dict(os.environ, **env)
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
+           "-k", "lnlike_golden or tile_boundaries or predict_golden or farm_vs_oracle"]
+    out = subprocess.run(cmd, cwd=root, env=child_env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
