@@ -241,6 +241,12 @@ def main():
                     "traffic": traffic,
                     "peak_source": "live DMMA.8x8x4 register-resident loop on all SMs (psoap_fp64_peak_tflops); "
                                    "MEASURED_PEAKS.json has no FP64 entry",
+                    "how": "achieved = algorithmic flops of one launch (K m (m+1), the DSYRK convention; the upper halves "
+                           "of the diagonal tiles are computed but not counted) / mean duration of 20 back-to-back launches of that kernel alone, "
+                           "CUDA events on its launch stream, taken inside bench.py right after the timed region "
+                           "(inside the evaluation graph the kernels of 32 branches overlap, so a per-kernel "
+                           "duration does not exist there); step_tflops_per_gpu = algorithmic flops of the timed "
+                           "region (sum over chunks of N^3/3 + 2N^2) / its measured time",
                     "step_tflops_per_gpu": step_tflops, "step_frac": step_tflops / peak.value,
                     "algorithmic_flops_per_eval": flops_total}
     if rank == 0:

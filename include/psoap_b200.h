@@ -98,7 +98,8 @@ int psoap_model_norb(int model);
 size_t psoap_lnlike_workspace_bytes(int64_t N);
 /* lnlike_f / lnlike_f_g / lnlike_f_g_h by ncomp.  All vectors are device pointers of length N; amp, l are
  * HOST arrays of ncomp doubles.  workspace_dev: >= psoap_lnlike_workspace_bytes(N) bytes, 256-byte aligned.
- * Negative amp or l gives lnlike = -inf without touching the device matrix (covariance.py:317,:339,:362). */
+ * Negative amp or l gives lnlike = -inf without touching the device matrix (covariance.py:317,:339,:362).
+ * N = 0 (an empty chunk, vectors may be null) gives -0.0 like the reference, whose sums then run over nothing. */
 int psoap_lnlike(int ncomp, int64_t N, const double *lwl_f_dev, const double *lwl_g_dev, const double *lwl_h_dev,
                  const double *fl_dev, const double *sigma_dev, const double *amp, const double *l, double mu_GP,
                  void *workspace_dev, size_t workspace_bytes, psoap_result *result_dev, void *stream);
@@ -146,9 +147,10 @@ int psoap_farm_destroy(psoap_farm *farm);
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* Register-resident DMMA.8x8x4 loop on all SMs: measured FP64 tensor-pipe peak in TFLOP/s (synchronous). */
 int psoap_fp64_peak_tflops(double *tflops_out);
-/* Times the dominant kernel (the DMMA trailing update, csrc/gemm.cuh syrk2_kernel) alone: `reps` launches of the
- * rank-K update (K = 128 or 256) of an m x m lower triangle, CUDA events on the launching stream.
- * flops_per_launch is the algorithmic count K m (m + 128). Synchronous. */
+/* Times the dominant kernel (the DMMA trailing update, csrc/gemm.cuh syrk3_kernel; syrk2_kernel under PSOAP_TMAP=0)
+ * alone: `reps` launches of the rank-K update (K a multiple of 128, up to 512 in the factorisation) of an m x m
+ * lower triangle, CUDA events on the launching stream.  flops_per_launch is the algorithmic count K m (m + 1)
+ * (DSYRK convention; the upper halves of the diagonal tiles are computed but not counted). Synchronous. */
 int psoap_bench_syrk(int64_t m, int K, int reps, double *avg_ms_out, double *flops_per_launch_out);
 /* Host-side replay of the trailing-update tile enumeration (csrc/gemm.cuh SyrkSrc::decode; no device work): the
  * (row tile r, 64-column tile jrel) of every tile of a launch over R row tiles for part 0 (all), 1 (first ncol1

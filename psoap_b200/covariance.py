@@ -38,6 +38,8 @@ def _lnlike(V11, lwls, fl, sigma, amps, ls, mu_GP):
     for v in vecs + [sg_d]:
         if v.dim() != 1 or v.numel() != N:
             raise ValueError("wavelength, flux and sigma vectors must be 1-D with the same length")
+    if N == 0:  # the reference's sums run over nothing: -0.5 * (0 + 0)
+        return -0.0
     nbytes = lib.psoap_lnlike_workspace_bytes(N)
     ws = _lib.workspace(nbytes + 256, "lnlike")
     res = torch.empty(4, dtype=torch.float64, device="cuda")

@@ -435,8 +435,7 @@ size_t psoap_lnlike_workspace_bytes(int64_t N) { return factor_ws_bytes(padded_d
 int psoap_lnlike(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h, const double* fl,
                  const double* sigma, const double* amp, const double* l, double mu_GP, void* workspace,
                  size_t workspace_bytes, psoap_result* result, void* stream) {
-    if (ncomp < 1 || ncomp > 3 || N < 1 || N > 200000 || !lwl_f || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h) || !fl ||
-        !sigma || !amp || !l || !result)
+    if (ncomp < 1 || ncomp > 3 || N < 0 || N > 200000 || !amp || !l || !result)
         return fail(PSOAP_ERR_ARG, "psoap_lnlike: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     GpParams gp;
@@ -445,6 +444,13 @@ int psoap_lnlike(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g,
         LAUNCH_CHECK();
         return PSOAP_OK;
     }
+    if (N == 0) {  // empty chunk: the reference's sums run over nothing, -0.5 * (0 + 0) = -0.0
+        write_result_kernel<<<1, 1, 0, st>>>((double*)result, -0.0, 0.0, 0.0, 0.0);
+        LAUNCH_CHECK();
+        return PSOAP_OK;
+    }
+    if (!lwl_f || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h) || !fl || !sigma)
+        return fail(PSOAP_ERR_ARG, "psoap_lnlike: null vector");
     if (!workspace || workspace_bytes < psoap_lnlike_workspace_bytes(N) || ((uintptr_t)workspace & 255))
         return fail(PSOAP_ERR_WORKSPACE, "psoap_lnlike: workspace too small or not 256-byte aligned");
     int rc = set_kernel_attributes();
@@ -469,8 +475,15 @@ struct HostCache {
 int psoap_lnlike_host(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h,
                       const double* fl, const double* sigma, const double* amp, const double* l, double mu_GP,
                       psoap_result* result) {
-    if (ncomp < 1 || ncomp > 3 || N < 1 || !lwl_f || !fl || !sigma || !result)
+    if (ncomp < 1 || ncomp > 3 || N < 0 || !amp || !l || !result)
         return fail(PSOAP_ERR_ARG, "psoap_lnlike_host: bad arguments");
+    if (N == 0) {  // empty chunk (see psoap_lnlike); no device work
+        GpParams gp;
+        result->lnlike = make_gp(ncomp, amp, l, &gp) ? -INFINITY : -0.0;
+        result->logdet = result->quad = result->info = 0.0;
+        return PSOAP_OK;
+    }
+    if (!lwl_f || !fl || !sigma) return fail(PSOAP_ERR_ARG, "psoap_lnlike_host: null vector");
     std::lock_guard<std::mutex> lock(g_hc.mu);
     const size_t vec = align_up((size_t)N * 8, 256);
     const size_t need = psoap_lnlike_workspace_bytes(N) + 5 * vec + 256;
@@ -752,7 +765,7 @@ int psoap_farm_destroy(psoap_farm* f) {
 
 // Times the trailing-update kernel (syrk2_kernel, the dominant kernel of the path) alone: `reps` launches of the
 // rank-K update (K = 128 or 256) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
-// stream.  flops_per_launch is the algorithmic count K * m * (m + 128) (2 flops per multiply-add, lower tiles).
+// stream.  flops_per_launch is the algorithmic count K * m * (m + 1) (DSYRK convention).
 int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
     if (m < NB || m % NB || reps < 1 || !avg_ms_out || K < NB || K % NB || K > 2048)
         return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
@@ -800,7 +813,9 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     cudaFree(W); cudaFree(P); cudaFree(y); cudaFree(r);
     *avg_ms_out = ms / reps;
-    if (flops_per_launch_out) *flops_per_launch_out = (double)K * (double)m * (double)(m + NB);
+    // algorithmic flops of the rank-K update of a lower triangle (the DSYRK convention k n (n+1)); the kernel also
+    // computes the upper halves of the diagonal tiles, K m 127 flops that are not counted
+    if (flops_per_launch_out) *flops_per_launch_out = (double)K * (double)m * (double)(m + 1);
     return PSOAP_OK;
 }
 

@@ -143,6 +143,27 @@ def test_lnlike_vs_oracle(model, n_epochs, n_pix, mask_frac, oracle, torch_cuda)
     assert got_dev == got
 
 
+def test_lnlike_empty_chunk(oracle, torch_cuda):
+    """A chunk whose mask removes every pixel: the reference returns -0.0 (fill, factorisation and sums over nothing),
+    -inf if a hyper-parameter is negative; so do the Python mirror and both C entry points."""
+    from psoap_b200 import _lib, covariance
+    e = np.empty(0)
+    ref = oracle.lnlike_f_g(np.empty((0, 0)), e, e, e, e, 0.1, 5.0, 0.05, 7.0)
+    got = covariance.lnlike_f_g(None, e, e, e, e, 0.1, 5.0, 0.05, 7.0)
+    assert got == ref == 0.0 and np.signbit(got) and np.signbit(ref)
+    assert covariance.lnlike_f_g(None, e, e, e, e, -0.1, 5.0, 0.05, 7.0) == -np.inf
+    lib = _lib.load()
+    res = _lib.PsoapResult()
+    amp, l = _lib.dbl_array([0.1, 0.05]), _lib.dbl_array([5.0, 7.0])
+    _lib.check(lib.psoap_lnlike_host(2, 0, None, None, None, None, None, amp, l, 1.0, ctypes.byref(res)))
+    assert res.lnlike == 0.0 and np.signbit(res.lnlike) and res.info == 0.0
+    dres = torch_cuda.full((4,), 7.0, dtype=torch_cuda.float64, device="cuda")
+    _lib.check(lib.psoap_lnlike(2, 0, None, None, None, None, None, amp, l, 1.0, None, 0, _lib.ptr(dres), _lib.stream_ptr()))
+    torch_cuda.cuda.synchronize()
+    out = dres.cpu().numpy()
+    assert out[0] == 0.0 and np.signbit(out[0]) and not out[1:].any()
+
+
 @pytest.mark.parametrize("n_pix", [127, 128, 129, 255, 256, 257, 383, 384, 385, 511, 513, 640, 897])
 def test_lnlike_tile_boundaries(n_pix, oracle, torch_cuda):
     """Sizes around the 128-row tile / 2- and 4-panel group boundaries (front padding, partial groups)."""
