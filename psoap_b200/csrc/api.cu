@@ -763,8 +763,8 @@ int psoap_farm_destroy(psoap_farm* f) {
     return PSOAP_OK;
 }
 
-// Times the trailing-update kernel (syrk2_kernel, the dominant kernel of the path) alone: `reps` launches of the
-// rank-K update (K = 128 or 256) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
+// Times the trailing-update kernel (syrk3_kernel, or syrk2_kernel under PSOAP_TMAP=0: the dominant kernel of the
+// path) alone: `reps` launches of the rank-K update (K a multiple of 128) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
 // stream.  flops_per_launch is the algorithmic count K * m * (m + 1) (DSYRK convention).
 int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
     if (m < NB || m % NB || reps < 1 || !avg_ms_out || K < NB || K % NB || K > 2048)

@@ -240,16 +240,12 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             double* sB = sA + BK * SA;
             const int k0 = pd.kbeg + p_kt * BK;
             mbar_arrive_expect_tx(&full[s], WARP_TX_BYTES);
-#ifdef PSOAP_FAKE_TMA   // timing experiment only (wrong data): one copy per warp per stage instead of four
-            tma_bulk_load(sA + warp * (WARP_TX_BYTES / 8), pd.Ai + (int64_t)(k0 + 2 * warp) * pd.lda, WARP_TX_BYTES, &full[s]);
-#else
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int c = 2 * warp + cc;
                 tma_bulk_load(sA + c * SA, pd.Ai + (int64_t)(k0 + c) * pd.lda, BI * 8, &full[s]);
                 tma_bulk_load(sB + c * SB, pd.Bj + (int64_t)(k0 + c) * pd.ldb, BJ * 8, &full[s]);
             }
-#endif
         }
         ++produced;
         if (++p_kt == pd.KT) {
