@@ -3,13 +3,15 @@
 //   acc[i][j] = sum_k Ai[i,k] * Bj[j,k]      128 x 64 output tile, 256 threads (8 warps, 32 x 32 each)
 //
 // B200-native structure:
-//   * operands are staged by the TMA engine: one cp.async.bulk (1-D bulk tensor copy, SASS UBLKCP) per matrix
-//     column segment, completing on an mbarrier with a transaction count; no thread moves operand data and
-//     there is no __syncthreads in the main loop.  Shared rows are padded (+4 doubles) so the m8n8k4 fragment
-//     loads are bank-conflict free.
-//   * producer duty is spread over the 8 warps (lane 0 of each issues the copies for 2 of the 16 k-columns of
-//     a stage), consumer release goes through a second set of mbarriers ("empty"), so warps drift freely and
-//     a stage is refilled one item after it was consumed.
+//   * operands are staged by the TMA engine through 2-D tensor maps: per stage of 16 k-columns ONE elected thread
+//     issues two cp.async.bulk.tensor.2d (SASS UTMALDG.2D), a box of 132 rows for the 128-row operand and one of
+//     68 rows for the 64-row operand, completing on an mbarrier with a transaction count; no thread moves operand
+//     data and there is no __syncthreads in the main loop.  The 4 extra rows of a box ARE the shared-memory row
+//     padding that makes the m8n8k4 fragment loads bank-conflict free (rows past the matrix edge arrive as zeros).
+//     (TMAP = false keeps the first staging: one 1-D cp.async.bulk, SASS UBLKCP, per matrix column segment, the
+//     48 copies of a stage spread over lane 0 of the 8 warps; 3 % slower, selected by PSOAP_TMAP=0.)
+//   * consumer release goes through a second set of mbarriers ("empty"), so warps drift freely and a stage is
+//     refilled two items after it was consumed.
 //   * CTAs are persistent (2 per SM) and the TMA pipeline runs ahead ACROSS tiles: the next tile's operands
 //     land while the current tile's epilogue (read-modify-write of C in HBM, prefetched into L2 at tile start)
 //     is in flight.
