@@ -238,7 +238,7 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
 // multiplies for the inverse part; no thread but the 16 column owners evaluates the reciprocal square root.
 // ------------------------------------------------------------------------------------------------------
 #ifdef PSOAP_POTRF_TRACE
-__device__ long long g_potrf_trace[8][128][5];   // [warp][step][phase] clock64 stamps (lab builds only)
+__device__ long long g_potrf_trace[8][128][8];   // [warp][step][phase] clock64 stamps (lab builds only)
 #define PSOAP_TRACE(ph) do { if ((tid & 31) == 0) g_potrf_trace[tid >> 5][j][ph] = clock64(); } while (0)
 #else
 #define PSOAP_TRACE(ph) do { } while (0)
@@ -278,9 +278,11 @@ __device__ __forceinline__ void potrf3_block_steps(double (&M)[8][8], int ti, in
             const int c = tid;
             Xs[c * XS + j] = (c < j) ? rb[c] * inv : ((c == j) ? inv : 0.0);
         }
+        PSOAP_TRACE(5);
         double li[8], w[8];
 #pragma unroll
         for (int p = JQ; p < 8; ++p) li[p] = cb[ti + 16 * p];
+        PSOAP_TRACE(6);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int c = tc + 16 * q;

@@ -18,11 +18,11 @@ int main() {
   for (int w = 0; w < 20; ++w) potrf_diag3_kernel<<<1, 256, POTRF_SMEM>>>(W, n, 0, 0, Linv, r, y, acc, info, nullptr, 1, res);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1); printf("potrf_diag3 avg %.2f us (%s)\n", ms * 1000 / 20, cudaGetErrorString(cudaGetLastError()));
-  static long long t[8][128][5];
+  static long long t[8][128][8];
   cudaMemcpyFromSymbol(t, g_potrf_trace, sizeof(t));
   for (int j : {5, 40, 64, 100, 120}) {
     printf("step %3d:", j);
-    for (int w : {0, 3, 7}) printf("  warp%d: pub %4lld | bar %4lld | loads %4lld | fma %4lld | total %4lld", w, t[w][j][1] - t[w][j][0], t[w][j][2] - t[w][j][1], t[w][j][3] - t[w][j][2], t[w][j][4] - t[w][j][3], t[w][j + 1][0] - t[w][j][0]);
+    for (int w : {0, 3, 7}) printf("  warp%d: pub %4lld | bar %4lld | xrow %4lld li %4lld w %4lld | fma %4lld | total %4lld", w, t[w][j][1] - t[w][j][0], t[w][j][2] - t[w][j][1], t[w][j][5] - t[w][j][2], t[w][j][6] - t[w][j][5], t[w][j][3] - t[w][j][6], t[w][j][4] - t[w][j][3], t[w][j + 1][0] - t[w][j][0]);
     printf("\n");
   }
   printf("whole loop: %lld cycles for 127 steps\n", t[0][127][0] - t[0][0][0]);
