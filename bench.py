@@ -84,7 +84,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = {"C4": 8}.get(args.workload, 1)
+    sample = {"C4": 16}.get(args.workload, 1)
     cmd = [sys.executable, "-m", "oracle.cpu_farm", "--config", args.workload, "--sample", str(sample), "--steps",
            str(args.steps), "--warmup", str(args.warmup)]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
@@ -130,12 +130,14 @@ def main():
     # CPU baseline first (rank 0, N=1 only), as its own process, before this process touches CUDA
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        sample = {"C4": 8}.get(args.workload, 1)
+        sample = {"C4": 16}.get(args.workload, 1)
         if args.workload == "C5":
             cpu_baseline = None
         else:
+            # bounded sample: 16 of the 256 chunks (one per host core on a 16-core box), 1 warm-up + 3 timed passes
             out = subprocess.run([sys.executable, "-m", "oracle.cpu_farm", "--config", args.workload, "--sample",
-                                  str(sample)], cwd=ROOT, capture_output=True, text=True)
+                                  str(sample), "--steps", "3", "--warmup", "1"], cwd=ROOT, capture_output=True,
+                                 text=True)
             if out.returncode == 0:
                 r = json.loads(out.stdout.strip().splitlines()[-1])
                 cpu_baseline = {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],

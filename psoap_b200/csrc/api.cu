@@ -158,7 +158,25 @@ struct Lanes {
     cudaStream_t side;   // may be null: no look-ahead
     cudaEvent_t e1, e2;
     int group = 0;       // panels per trailing update (2 or 4); 0 = choose from the problem size
+    int pdl = 0;         // grids of at most this many CTAs are launched with programmatic stream serialization (0: none)
 };
+
+// Launch with or without the programmatic-stream-serialization attribute: with it the kernel may become resident
+// while its predecessor in the stream still runs, and waits in pdl_wait() (common.cuh).  Only SMALL grids are
+// pre-staged: a waiting CTA holds its SM slot, which is free when the chain is the only work (small matrices, the
+// tail of a large one) and costly while a big trailing update wants every slot.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, int pdl_max,
+                     Args&&... args) {
+    const bool pdl = (int)grid <= pdl_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
 // (T_elim == T_total: plain Cholesky).  The trailing block is left holding the Schur complement.
@@ -198,16 +216,16 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
             potrf_diag5_kernel<<<1, 256, POTRF5_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
                                                            ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
         else
-            potrf_diag3_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
-                                                          ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
+            launch_k(potrf_diag3_kernel, 1, 256, POTRF_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv, ws.rvec,
+                     ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
     };
     auto trsm = [&](cudaStream_t s, int kb, int q, int col0) {
         const int R = T_total - kb - 1;
         TrsmSrc src;
         src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
         src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
-        if (tmap) trsm3_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R, mapW, mapLinv);
-        else trsm2_kernel<<<persistent_ctas(2 * R), 256, GEMM_SMEM, s>>>(src, 2 * R);
+        if (tmap) launch_k(trsm3_kernel, persistent_ctas(2 * R), 256, GEMM_SMEM, s, ln.pdl, src, 2 * R, mapW, mapLinv);
+        else launch_k(trsm2_kernel, persistent_ctas(2 * R), 256, GEMM_SMEM, s, ln.pdl, src, 2 * R);
     };
     // update of row tiles [row0, T_total) with k range [kbeg, kend) of group buffer q; the residual blocks (if
     // ykb >= 0) apply panel ykb, whose columns start at res_col0 in the buffer
@@ -223,12 +241,12 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         // continuously and the high-priority side stream (next group's potrf/trsm) is scheduled into them.
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
+        const double* yk = ws.y + (int64_t)std::max(ykb, 0) * NB;
         if (tmap)
-            syrk3_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
-                                                              ws.rvec, res_col0, mapPa[q & 1], mapPb[q & 1]);
+            launch_k(syrk3_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
+                     mapPa[q & 1], mapPb[q & 1]);
         else
-            syrk2_kernel<<<nctas + nres, 256, GEMM_SMEM, s>>>(src, ntiles, nctas, nres, ws.y + (int64_t)std::max(ykb, 0) * NB,
-                                                              ws.rvec, res_col0);
+            launch_k(syrk2_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0);
         ++g_launches;
     };
     const int ngroups = (T_elim + G - 1) / G;
@@ -318,6 +336,8 @@ int get_lanes(cudaStream_t user, Lanes* ln) {
     const char* la_env = getenv("PSOAP_LOOKAHEAD");
     const bool lookahead = la_env ? (atoi(la_env) != 0) : true;
     ln->main = user; ln->side = lookahead ? sl.side : nullptr; ln->e1 = sl.e1; ln->e2 = sl.e2;
+    const char* pdl_env = getenv("PSOAP_PDL");
+    ln->pdl = pdl_env ? atoi(pdl_env) : 64;
     return PSOAP_OK;
 }
 

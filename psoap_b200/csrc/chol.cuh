@@ -320,6 +320,8 @@ potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     const int tid = threadIdx.x;
     const int ti = tid & 15, tc = tid >> 4;
     const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
+    pdl_trigger();   // one CTA: the panel solve may become resident on the other SMs while this block is factored
+    pdl_wait();
 
     double M[8][8];
 #pragma unroll

@@ -81,6 +81,13 @@ __device__ __forceinline__ double z_at(const ZSource& zs, int c, int64_t i) {
     return __dadd_rn(zs.lwl[0][i], __ddiv_rn(-v, C_KMS));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still running; it must not touch the predecessor's
+// output before pdl_wait().  pdl_trigger() in the predecessor lets the dependent start early.  Both are no-ops
+// for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)

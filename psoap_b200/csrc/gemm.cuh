@@ -358,11 +358,15 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 // Persistent launch geometry: `nctas` CTAs walk the tiles round-robin.
 __global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) {
     extern __shared__ __align__(128) double sm[];
+    pdl_trigger();   // small grid: let the trailing update become resident behind it
+    pdl_wait();
     gemm_persistent<0, false>(src, ntiles, blockIdx.x, gridDim.x, sm);
 }
 __global__ void __launch_bounds__(256, 2)
 trsm3_kernel(TrsmSrc src, int ntiles, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapLinv) {
     extern __shared__ __align__(128) double sm[];
+    pdl_trigger();   // small grid: let the trailing update become resident behind it
+    pdl_wait();
     gemm_persistent<0, true>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
 }
 
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(256, 2)
 syrk2_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0) {
     extern __shared__ __align__(128) double sm[];
+    pdl_wait();
     if ((int)blockIdx.x >= nres) {
         gemm_persistent<1, false>(src, ntiles, (int)blockIdx.x - nres, nctas, sm);
     } else {
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(256, 2)
 syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb) {
     extern __shared__ __align__(128) double sm[];
+    pdl_wait();
     if ((int)blockIdx.x >= nres) {
         // same buffer, two boxes: 132 rows for the 128-row operand, 68 rows for the 64-row one
         gemm_persistent<1, true>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);

@@ -458,8 +458,9 @@ def test_farm_many_proposals(oracle, torch_cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"PSOAP_TMAP": "0"}, {"PSOAP_POTRF": "5"}, {"PSOAP_POTRF": "1", "PSOAP_GROUP": "2"}],
-                         ids=["per-column-tma", "blocked-potrf", "first-potrf"])
+@pytest.mark.parametrize("env", [{"PSOAP_TMAP": "0"}, {"PSOAP_POTRF": "5"}, {"PSOAP_POTRF": "1", "PSOAP_GROUP": "2"},
+                                 {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"}],
+                         ids=["per-column-tma", "blocked-potrf", "first-potrf", "no-pdl-no-lookahead", "pdl-everywhere"])
 def test_alternative_kernel_paths(env, torch_cuda):
     """The library's environment switches select alternative kernels for the same contract (the per-column bulk-copy
     GEMM staging, the blocked diagonal factorisation, the first diagonal kernel).  They are read once at load time,
