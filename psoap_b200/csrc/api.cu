@@ -593,8 +593,50 @@ struct psoap_farm {
     std::vector<cudaStream_t> side_streams;
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> side_events;
+    std::vector<double*> item_vel;    // device velocity table of each item
+    bool lookahead = false;
+    bool direct = false;              // issue the kernels on every call instead of replaying the captured graph
     int launches = 0;
 };
+
+namespace {
+// Issues one evaluation onto the farm's streams, rooted at s0: the orbit kernel for every item, then the per-chunk
+// pipelines on the branch streams, joined back into s0.  Runs under stream capture (graph mode) or for real
+// (direct mode, which adds programmatic dependent launch on the small grids).
+int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
+    const int nbranch = f->nbranch, nchunks = f->nchunks;
+    orbit_farm_kernel<<<f->nitems, 64, 0, s0>>>(f->model, f->p_buf, f->descs);
+    ++g_launches;
+    cudaEventRecord(f->events[nbranch], s0);
+    int rc = PSOAP_OK;
+    for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
+        cudaStream_t sb = f->streams[b];
+        cudaStreamWaitEvent(sb, f->events[nbranch], 0);
+        for (int it : f->branch_items[b]) {
+            const psoap_chunk& ch = f->chunks[it % nchunks];
+            GpParams gp;
+            gp.dev = f->p_buf + (size_t)(it / nchunks) * P_STRIDE + f->norb;
+            for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
+            ZSource zs;
+            zs.lwl[0] = ch.lwl; zs.lwl[1] = nullptr; zs.lwl[2] = nullptr;
+            zs.epoch = ch.epoch; zs.vel = f->item_vel[it]; zs.n_epochs = ch.n_epochs; zs.shift = 1;
+            FactorWs ws = f->branch_ws[b];
+            ws.Nt = padded_dim(ch.N);
+            Lanes ln;
+            ln.main = sb;
+            ln.side = f->lookahead ? f->side_streams[b] : nullptr;
+            ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
+            ln.group = f->lookahead ? 0 : 4;
+            ln.pdl = pdl;
+            rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, f->mu, gp, ws, f->flags + it, f->results + 4 * it);
+            if (rc) break;
+        }
+        cudaEventRecord(f->events[b], sb);
+        cudaStreamWaitEvent(s0, f->events[b], 0);
+    }
+    return rc;
+}
+}  // namespace
 
 namespace {
 // item = prop * nchunks + chunk
@@ -708,38 +750,22 @@ int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const ps
     }
     cudaStream_t s0 = f->streams[nbranch];
     const int64_t before = g_launches.load();
+    const char* la_env = getenv("PSOAP_FARM_LOOKAHEAD");
+    f->lookahead = la_env ? (atoi(la_env) != 0) : (nbranch < 8);
+    f->item_vel.resize(nitems);
+    for (int it = 0; it < nitems; ++it) f->item_vel[it] = hd[it].vel;
+    // Graph replay removes every launch gap, which wins for short chains (N = 4000: 2.57 vs 2.75 ms); for a farm of
+    // a few LARGE chunks the directly issued pipeline is faster (N = 9000: 10.5 vs 11.3 ms: the side stream's
+    // priority and the pre-staged small grids do their job there).  PSOAP_FARM_DIRECT=0|1 overrides.
+    {
+        int64_t nmax = 0;
+        for (int i = 0; i < nchunks; ++i) nmax = std::max<int64_t>(nmax, chunks[i].N);
+        const char* de = getenv("PSOAP_FARM_DIRECT");
+        f->direct = de ? (atoi(de) != 0) : (f->lookahead && nmax >= 7000);
+    }
     e = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { psoap_farm_destroy(f); return fail(PSOAP_ERR_CUDA, std::string("begin capture: ") + cudaGetErrorString(e)); }
-    orbit_farm_kernel<<<nitems, 64, 0, s0>>>(model, f->p_buf, f->descs);
-    ++g_launches;
-    cudaEventRecord(f->events[nbranch], s0);
-    rc = PSOAP_OK;
-    const char* la_env = getenv("PSOAP_FARM_LOOKAHEAD");
-    const bool lookahead = la_env ? (atoi(la_env) != 0) : (nbranch < 8);
-    for (int b = 0; b < nbranch && rc == PSOAP_OK; ++b) {
-        cudaStream_t sb = f->streams[b];
-        cudaStreamWaitEvent(sb, f->events[nbranch], 0);
-        for (int it : f->branch_items[b]) {
-            const psoap_chunk& ch = f->chunks[it % nchunks];
-            GpParams gp;
-            gp.dev = f->p_buf + (size_t)(it / nchunks) * P_STRIDE + f->norb;
-            for (int c = 0; c < 3; ++c) { gp.amp[c] = 0; gp.l[c] = 1; }
-            ZSource zs;
-            zs.lwl[0] = ch.lwl; zs.lwl[1] = nullptr; zs.lwl[2] = nullptr;
-            zs.epoch = ch.epoch; zs.vel = hd[it].vel; zs.n_epochs = ch.n_epochs; zs.shift = 1;
-            FactorWs ws = f->branch_ws[b];
-            ws.Nt = padded_dim(ch.N);
-            Lanes ln;
-            ln.main = sb;
-            ln.side = lookahead ? f->side_streams[b] : nullptr;
-            ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
-            ln.group = lookahead ? 0 : 4;
-            rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, mu_GP, gp, ws, f->flags + it, f->results + 4 * it);
-            if (rc) break;
-        }
-        cudaEventRecord(f->events[b], sb);
-        cudaStreamWaitEvent(s0, f->events[b], 0);
-    }
+    rc = farm_issue(f, s0, 0);
     e = cudaStreamEndCapture(s0, &f->graph);
     f->launches = (int)(g_launches.load() - before);
     g_launches = before;  // capture is not execution
@@ -763,8 +789,21 @@ int psoap_farm_lnprob(psoap_farm* f, const double* p_dev, psoap_result* results_
     // p_dev: [nprop][np] contiguous -> [nprop][P_STRIDE]
     CUDA_TRY(cudaMemcpy2DAsync(f->p_buf, P_STRIDE * 8, p_dev, (size_t)np * 8, (size_t)np * 8, f->nprop,
                                cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaGraphLaunch(f->exec, st));
-    g_launches += f->launches;
+    if (f->direct) {
+        // the pipelines run on the farm's own streams: fork from the caller's stream and join back into it
+        cudaStream_t s0 = f->streams[f->nbranch];
+        cudaEvent_t fork = f->events[f->nbranch];
+        CUDA_TRY(cudaEventRecord(fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(s0, fork, 0));
+        const char* pdl_env = getenv("PSOAP_PDL");
+        int rc = farm_issue(f, s0, pdl_env ? atoi(pdl_env) : 64);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(fork, s0));
+        CUDA_TRY(cudaStreamWaitEvent(st, fork, 0));
+    } else {
+        CUDA_TRY(cudaGraphLaunch(f->exec, st));
+        g_launches += f->launches;
+    }
     CUDA_TRY(cudaMemcpyAsync(results_dev, f->results, (size_t)f->nitems * sizeof(psoap_result), cudaMemcpyDeviceToDevice, st));
     return PSOAP_OK;
 }
