@@ -261,6 +261,26 @@ def test_farm_vs_oracle(oracle, torch_cuda):
         farm.close()
 
 
+def test_farm_direct_mode_large_chunk(oracle, torch_cuda):
+    """A one-chunk farm with N >= 7000 issues its pipeline directly instead of replaying the graph (api.cu
+    psoap_farm.direct); the value must be the one the operator surface gives for the same chunk, call after call."""
+    from psoap_b200 import covariance, synthetic
+    from psoap_b200.farm import ChunkFarm
+    ch = synthetic.make_chunk("SB2", 22, 320, seed=4)          # N = 7040
+    p = synthetic.default_params("SB2")
+    farm = ChunkFarm("SB2", [ch])
+    got = [farm.lnprob(p) for _ in range(3)]
+    assert got[0] == got[1] == got[2]
+    vel = oracle.get_velocities("SB2", p[:7], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    ref = covariance.lnlike_f_g(None, lwls[0], lwls[1], ch["fl"], ch["sigma"], *p[7:])
+    assert rel_close(got[0], ref, LNLIKE_RTOL), (got[0], ref)
+    p2 = p.copy(); p2[1] *= 1.1                                 # another proposal through the same farm
+    vel2 = oracle.get_velocities("SB2", p2[:7], ch["date1D"])
+    lw2 = oracle.replicate_wls(ch["lwl"], vel2, ch["mask"])
+    assert rel_close(farm.lnprob(p2), covariance.lnlike_f_g(None, lw2[0], lw2[1], ch["fl"], ch["sigma"], *p2[7:]), LNLIKE_RTOL)
+
+
 def test_farm_partition_matches_single(oracle, torch_cuda):
     """Emulated ranks on one GPU: the per-rank vectors (zero outside own chunks) sum to the single-rank answer."""
     from psoap_b200 import synthetic
