@@ -1,4 +1,4 @@
-"""Time the farm on a subset of C4 (what one rank of an 8-GPU run holds): python tools/farm_subset_time.py [stride]"""
+"""Time the farm on a subset of C4 (what one rank of a W-GPU run holds): python tools/farm_subset_time.py [W] [nbranch]"""
 import os
 import sys
 import time
@@ -14,7 +14,8 @@ model, chunks = synthetic.config_chunks("C4")
 parts = lpt_partition([chunk_cost(c["N"]) for c in chunks], world)
 mine = [chunks[i] for i in sorted(parts[0])]
 p = synthetic.default_params(model)
-farm = ChunkFarm(model, mine)
+nbranch = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+farm = ChunkFarm(model, mine, nbranch=nbranch)
 for _ in range(3):
     farm.lnprob(p)
 torch.cuda.synchronize()
@@ -23,4 +24,4 @@ for _ in range(5):
     farm.lnprob(p)
 dt = (time.perf_counter() - t0) / 5
 fl = sum(c["N"] ** 3 / 3 for c in mine)
-print("rank 0 of %d: %d chunks, %.2f ms per evaluation, %.2f TFLOP/s" % (world, len(mine), dt * 1e3, fl / dt * 1e-12))
+print("rank 0 of %d: %d chunks, nbranch %d, %.2f ms per evaluation, %.2f TFLOP/s" % (world, len(mine), nbranch, dt * 1e3, fl / dt * 1e-12))
