@@ -58,36 +58,31 @@ def get_labels(model, fix_params):
 
 
 def gelman_rubin(samplelist, verbose=False):
-    """psoap/utils.py:99-163 (BDA3 p.284, split chains).  The reference prints an astropy table and returns
-    nothing; this returns (mean, std_hat, R_hat) so the numbers can be used, and prints only when asked."""
-    full_iterations = len(samplelist[0])
-    assert full_iterations % 2 == 0, "Number of iterations must be even. Try cutting off a different number of burn in samples."
-    shape = samplelist[0].shape
-    for flatchain in samplelist:
-        assert len(flatchain) == full_iterations, "Not all chains have the same number of iterations!"
-        assert flatchain.shape == shape, "Not all flatchains have the same shape!"
-    n = full_iterations // 2
-    m = 2 * len(samplelist)
-    nparams = samplelist[0].shape[-1]
-    chains = np.empty((n, m, nparams))
-    for k, flatchain in enumerate(samplelist):
-        chains[:, 2 * k, :] = flatchain[:n]
-        chains[:, 2 * k + 1, :] = flatchain[n:]
-    avg_phi_j = np.mean(chains, axis=0, dtype="f8")
-    avg_phi = np.mean(chains, axis=(0, 1), dtype="f8")
-    B = n / (m - 1.0) * np.sum((avg_phi_j - avg_phi) ** 2, axis=0, dtype="f8")
-    s2j = 1.0 / (n - 1.0) * np.sum((chains - avg_phi_j) ** 2, axis=0, dtype="f8")
-    W = 1.0 / m * np.sum(s2j, axis=0, dtype="f8")
-    var_hat = (n - 1.0) / n * W + B / n
+    """Split-chain potential scale reduction (BDA3 p.284), the statistic psoap/utils.py:99-163 prints.  Takes the
+    same list of equally shaped flatchains [iterations, n_params] (even number of iterations); returns
+    (mean, std_hat, R_hat) per parameter instead of printing an astropy table, and prints only when asked."""
+    chains = np.asarray(samplelist, dtype=np.float64)
+    if chains.ndim != 3:
+        raise AssertionError("flatchains must all have the same shape [iterations, n_params]")
+    n_iter = chains.shape[1]
+    if n_iter % 2:
+        raise AssertionError("the number of iterations must be even; cut a different number of burn-in samples")
+    half = n_iter // 2
+    # every chain is split in two: [2 * n_chains, half, n_params]
+    split = np.concatenate([chains[:, :half], chains[:, half:]], axis=0)
+    n_split = split.shape[0]
+    chain_mean = split.mean(axis=1)
+    grand_mean = chain_mean.mean(axis=0)
+    between = half / (n_split - 1.0) * ((chain_mean - grand_mean) ** 2).sum(axis=0)
+    within = split.var(axis=1, ddof=1).mean(axis=0)
+    var_hat = (half - 1.0) / half * within + between / half
     std_hat = np.sqrt(var_hat)
-    R_hat = np.sqrt(var_hat / W)
+    R_hat = np.sqrt(var_hat / within)
     if verbose:
-        print("Value:", avg_phi)
-        print("Uncertainty:", std_hat)
-        print("R_hat: {}".format(R_hat))
+        print("value", grand_mean, "uncertainty", std_hat, "R_hat", R_hat)
         if np.any(R_hat >= 1.1):
-            print("You might consider running the chain for longer. Not all R_hats are less than 1.1.")
-    return avg_phi, std_hat, R_hat
+            print("not every R_hat is below 1.1: consider running the chains for longer")
+    return grand_mean, std_hat, R_hat
 
 
 def estimate_covariance(flatchain, ndim=0):
