@@ -219,7 +219,10 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 
     // ---- producer cursor: which (tile, k-chunk) the next issued stage belongs to.  The stage consumed at
     // item g is refilled at item g + 2 (LAG), so the producing lane practically never spins on the slowest warp.
-    constexpr int LAG = 2;
+#ifndef PSOAP_LAG
+#define PSOAP_LAG 2
+#endif
+    constexpr int LAG = PSOAP_LAG;
     int p_tile = first_tile, p_kt = 0, produced = 0;
     bool p_valid = p_tile < ntiles;
     TileDesc pd;
