@@ -51,7 +51,9 @@ class ChunkFarm:
         self.n_params = _lib.N_ORB[model] + 2 * _lib.NCOMP[model]
         self.rank, self.world_size, self.group = rank, world_size, process_group
         self.parts = lpt_partition([chunk_cost(len(ch["fl"])) for ch in chunks], world_size)
-        self.mine = sorted(self.parts[rank])
+        # a chunk whose mask removed every pixel contributes -0.0 in the reference (sums over nothing): it takes no
+        # device work here and its entry of the per-chunk vector stays 0
+        self.mine = [i for i in sorted(self.parts[rank]) if len(chunks[i]["fl"]) > 0]
         # every chunk vector lives in ONE pinned host buffer and ONE device buffer (256-byte aligned slices), so a
         # refresh of the resident data is a single host->device copy
         hosts, offsets, total = [], [], 0

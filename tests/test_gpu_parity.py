@@ -261,6 +261,22 @@ def test_farm_vs_oracle(oracle, torch_cuda):
         farm.close()
 
 
+def test_farm_skips_empty_chunk(oracle, torch_cuda):
+    """A fully masked chunk adds -0.0 in the reference; the farm gives the same total with or without it."""
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import ChunkFarm
+    chunks = [synthetic.make_chunk("SB2", 4, 50, seed=21 + i) for i in range(3)]
+    empty = dict(chunks[0], lwl=np.empty(0), fl=np.empty(0), sigma=np.empty(0),
+                 mask=np.zeros_like(chunks[0]["mask"], dtype=bool))
+    p = synthetic.default_params("SB2")
+    full = ChunkFarm("SB2", chunks).lnprob(p)
+    with_empty = ChunkFarm("SB2", chunks[:1] + [empty] + chunks[1:])
+    assert with_empty.lnprob(p) == full
+    per_chunk = with_empty.chunk_lnlikes(p).cpu().numpy()
+    assert per_chunk.shape == (4,) and per_chunk[1] == 0.0 and np.all(per_chunk[[0, 2, 3]] != 0.0)
+    assert rel_close(full, oracle.farm_lnprob("SB2", p, chunks)[0], LNLIKE_RTOL)
+
+
 def test_farm_direct_mode_large_chunk(oracle, torch_cuda):
     """A one-chunk farm with N >= 7000 issues its pipeline directly instead of replaying the graph (api.cu
     psoap_farm.direct); the value must be the one the operator surface gives for the same chunk, call after call."""
