@@ -25,43 +25,63 @@ __device__ __forceinline__ void gp_coeffs(const GpParams& gp, int c, double& amp
     p2 = __ddiv_rn(-0.5 * C_KMS2, __dmul_rn(l, l));
 }
 
+// 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic).
+__device__ const double EXP2_64_TAB[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+// Every kernel that evaluates covariance terms keeps a copy of the table in shared memory (lanes index it with
+// different j): call before the kernel's first __syncthreads().
+__device__ __forceinline__ void load_exp_table(double* tab_sm) {
+    if (threadIdx.x < 64) tab_sm[threadIdx.x] = EXP2_64_TAB[threadIdx.x];
+}
+
 // exp(x) for x <= 0 without a branch (the squared-exponential argument is never positive).  libdevice's exp takes a
 // slow path below -708 — which is where most covariance entries live — and its branches keep the compiler from
-// interleaving the independent evaluations of an unrolled fill loop.  Cody-Waite reduction x = n ln2 + r,
-// |r| <= ln2/2, degree-12 Taylor polynomial (truncation 1.7e-16), result scaled by 2^n in two steps so that the
-// subnormal range rounds once.  Maximum relative error 3.2e-16 against glibc over [-745, 0] (2e7 samples, host copy
-// of this code); exactly 0 below -745.2 and NaN for NaN, like exp.
-__device__ __forceinline__ double exp_neg(double x) {
+// interleaving the independent evaluations of an unrolled fill loop.  Table-driven: x = (64 e + j) ln2/64 + r with
+// |r| <= ln2/128 (Cody-Waite, two-word ln2/64), exp(x) = 2^e * T[j] * (1 + r + ... + r^5/120) (truncation 3.5e-17),
+// scaled by 2^e in two steps so that the subnormal range rounds once: 13 FP64 operations against libdevice's ~21.
+// Maximum relative error 2.2e-16 against glibc over [-745, 0] (3e7 samples, host copy of this code); exactly 0
+// below -745.2 and NaN for NaN, like exp.
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab_sm) {
     x = (x < -750.0) ? -750.0 : x;
-    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the integer n lands in the low word of t
-    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the integer 64 e + j lands in the low word of t
+    const double t = fma(x, 92.33248261689365676830, SHIFT);            // 64 / ln 2
     const double n = t - SHIFT;
-    double r = fma(n, -6.93147180369123816490e-01, x);
-    r = fma(n, -1.90821492927058770002e-10, r);
-    double p = 1.0 / 479001600.0;
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    double r = fma(n, -1.083042469326755963266e-02, x);                  // ln2/64, high word (21 trailing zero bits)
+    r = fma(n, -2.981585826985293281284e-12, r);                         // ln2/64, low word
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double p = q * r;                                              // exp(r) - 1
     const int ni = __double2loint(t);
-    const int n1 = ni >> 1, n2 = ni - n1;
-    const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
-    const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
-    return (p * s1) * s2;
+    const double T = tab_sm[ni & 63];
+    const double v = fma(T, p, T);
+    const int e = ni >> 6, e1 = e >> 1, e2 = e - e1;
+    const double s1 = __hiloint2double((e1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((e2 + 1023) << 20, 0);
+    return (v * s1) * s2;
 }
 
 // One covariance term amp2 * exp((p2 * r) * r), r = zj - zi (matrix_functions.pyx:47-49).
-__device__ __forceinline__ double se_term(double amp2, double p2, double zi, double zj) {
+__device__ __forceinline__ double se_term(double amp2, double p2, double zi, double zj, const double* __restrict__ tab_sm) {
     double r = __dsub_rn(zj, zi);
-    return __dmul_rn(amp2, exp_neg(__dmul_rn(__dmul_rn(p2, r), r)));
+    return __dmul_rn(amp2, exp_neg(__dmul_rn(__dmul_rn(p2, r), r), tab_sm));
 }
 
 // Where the ln-wavelength of component c at data index i comes from: either per-component vectors

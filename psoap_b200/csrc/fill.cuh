@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) fill_lower_kernel(double* __restrict__ W,
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;
     __shared__ double zj[NCOMP][NB];
+    __shared__ double etab[64];
+    load_exp_table(etab);
     const int tid = threadIdx.x;
     if (tid < NB) {
         int pj = bj * NB + tid;
@@ -65,9 +67,9 @@ __global__ void __launch_bounds__(256) fill_lower_kernel(double* __restrict__ W,
             } else if (pi == pj) {
                 v[e] = dg[e];
             } else {
-                double cov = se_term(amp2[0], p2[0], zi[0][e], zj[0][jl]);
+                double cov = se_term(amp2[0], p2[0], zi[0][e], zj[0][jl], etab);
 #pragma unroll
-                for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zi[c][e], zj[c][jl]));
+                for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zi[c][e], zj[c][jl], etab));
                 v[e] = cov;
             }
         }
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(256) fill_full_kernel(double* __restrict__ mat
     if (bj > bi) return;
     __shared__ double zi[NCOMP][64], zj[NCOMP][64];
     __shared__ double tile[64][65];
+    __shared__ double etab[64];
+    load_exp_table(etab);
     const int tid = threadIdx.x;
     if (tid < 64) {
         int i = bi * 64 + tid, j = bj * 64 + tid;
@@ -114,9 +118,9 @@ __global__ void __launch_bounds__(256) fill_full_kernel(double* __restrict__ mat
         } else {
             // r = z[j] - z[i]; for i < j (diagonal tiles only) this is the negated distance of the mirrored
             // pair, and (p2*r)*r is bit-identical under r -> -r.
-            cov = se_term(amp2[0], p2[0], zi[0][il], zj[0][tx]);
+            cov = se_term(amp2[0], p2[0], zi[0][il], zj[0][tx], etab);
 #pragma unroll
-            for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zi[c][il], zj[c][tx]));
+            for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zi[c][il], zj[c][tx], etab));
         }
         tile[il][tx] = cov;
         if (i < N && j < N) mat[(int64_t)i * ld + j] = cov;
@@ -141,6 +145,8 @@ template <int NCOMP>
 __global__ void __launch_bounds__(256) fill_v12_kernel(double* __restrict__ mat, int64_t ld, int M, int N, V12Src src,
                                                        GpParams gp) {
     __shared__ double zr[NCOMP][64];
+    __shared__ double etab[64];
+    load_exp_table(etab);
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * 64;
     const int j = blockIdx.x * 64 + (tid & 63);
@@ -158,9 +164,9 @@ __global__ void __launch_bounds__(256) fill_v12_kernel(double* __restrict__ mat,
         const int il = ty + 4 * r;
         const int i = i0 + il;
         if (i < M && j < N) {
-            double cov = se_term(amp2[0], p2[0], zr[0][il], zc[0]);
+            double cov = se_term(amp2[0], p2[0], zr[0][il], zc[0], etab);
 #pragma unroll
-            for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zr[c][il], zc[c]));
+            for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zr[c][il], zc[c], etab));
             mat[(int64_t)i * ld + j] = cov;
         }
     }
