@@ -54,6 +54,24 @@ __global__ void __launch_bounds__(256) fill_lower_kernel(double* __restrict__ W,
     }
     __syncthreads();
     const int cg = tid >> 6;
+    // Interior tiles (strictly below the diagonal, clear of the identity padding) are 95 % of the tiles of a large
+    // matrix: no per-entry case analysis there.
+    if (bi != bj && (bj > 0 || pad == 0)) {
+#pragma unroll 4
+        for (int cc = 0; cc < 32; ++cc) {
+            const int jl = cc * 4 + cg;
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double cov = se_term(amp2[0], p2[0], zi[0][e], zj[0][jl], etab);
+#pragma unroll
+                for (int c = 1; c < NCOMP; ++c) cov = __dadd_rn(cov, se_term(amp2[c], p2[c], zi[c][e], zj[c][jl], etab));
+                v[e] = cov;
+            }
+            *reinterpret_cast<double2*>(W + pi0 + (int64_t)(bj * NB + jl) * ld) = make_double2(v[0], v[1]);
+        }
+        return;
+    }
 #pragma unroll 4
     for (int cc = 0; cc < 32; ++cc) {
         const int jl = cc * 4 + cg;
