@@ -71,6 +71,8 @@ int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
 int g_potrf_version = 3;
 int g_pf_mode = 2;
+int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
+int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
 int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
@@ -105,6 +107,8 @@ int set_kernel_attributes() {
                 g_use_tmap = 0;
             cudaGetLastError();
         }
+        if (const char* c = getenv("PSOAP_LOOKAHEAD")) g_lookahead = atoi(c);
+        if (const char* c = getenv("PSOAP_PDL")) g_pdl = atoi(c);
         if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
     });
     if (g_attr_status != 0)
@@ -333,11 +337,9 @@ int get_lanes(cudaStream_t user, Lanes* ln) {
         CUDA_TRY(cudaEventCreateWithFlags(&sl.e1, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&sl.e2, cudaEventDisableTiming));
     }
-    const char* la_env = getenv("PSOAP_LOOKAHEAD");
-    const bool lookahead = la_env ? (atoi(la_env) != 0) : true;
-    ln->main = user; ln->side = lookahead ? sl.side : nullptr; ln->e1 = sl.e1; ln->e2 = sl.e2;
-    const char* pdl_env = getenv("PSOAP_PDL");
-    ln->pdl = pdl_env ? atoi(pdl_env) : 64;
+    // g_lookahead / g_pdl were read from the environment once, in set_kernel_attributes()
+    ln->main = user; ln->side = g_lookahead ? sl.side : nullptr; ln->e1 = sl.e1; ln->e2 = sl.e2;
+    ln->pdl = g_pdl;
     return PSOAP_OK;
 }
 
@@ -795,8 +797,7 @@ int psoap_farm_lnprob(psoap_farm* f, const double* p_dev, psoap_result* results_
         cudaEvent_t fork = f->events[f->nbranch];
         CUDA_TRY(cudaEventRecord(fork, st));
         CUDA_TRY(cudaStreamWaitEvent(s0, fork, 0));
-        const char* pdl_env = getenv("PSOAP_PDL");
-        int rc = farm_issue(f, s0, pdl_env ? atoi(pdl_env) : 64);
+        int rc = farm_issue(f, s0, g_pdl);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(fork, s0));
         CUDA_TRY(cudaStreamWaitEvent(st, fork, 0));
