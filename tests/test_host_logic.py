@@ -193,3 +193,55 @@ def test_chain_diagnostics():
     fc = rng.normal(size=(2000, 3)) * np.array([1.0, 2.0, 0.5])
     oj = utils.estimate_covariance(fc)
     assert np.allclose(oj, 2.38 ** 2 / 3 * np.cov(fc, rowvar=0))
+
+
+# ------------------------------------------------------------------------------------- property-based checks
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(min_value=1, max_value=9000), min_size=1, max_size=80), st.integers(min_value=1, max_value=8))
+def test_lpt_partition_properties(Ns, nparts):
+    """Every chunk is assigned exactly once, empty parts only when there are fewer chunks than parts, and the largest
+    load obeys Graham's bound for greedy list scheduling: max <= sum/m + (1 - 1/m) * largest item."""
+    from psoap_b200.farm import chunk_cost, lpt_partition
+    costs = [chunk_cost(n) for n in Ns]
+    parts = lpt_partition(costs, nparts)
+    assert len(parts) == nparts
+    assert sorted(i for p in parts for i in p) == list(range(len(Ns)))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) <= (sum(costs) / nparts + (1.0 - 1.0 / nparts) * max(costs)) * (1 + 1e-12)
+    if len(Ns) >= nparts:
+        assert all(len(p) > 0 for p in parts)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(min_value=1, max_value=12), st.integers(min_value=1, max_value=40), st.integers(min_value=0, max_value=2 ** 31 - 1))
+def test_epoch_index_properties(n_epochs, n_pix, seed):
+    """epoch_index(mask)[k] is the row of the k-th kept pixel of the row-major flattening (data.py:61), for any mask
+    including all-false rows and the empty mask."""
+    from psoap_b200.data import epoch_index
+    rng = np.random.default_rng(seed)
+    mask = rng.uniform(size=(n_epochs, n_pix)) > rng.uniform()
+    ep = epoch_index(mask)
+    assert ep.dtype == np.int32 and ep.shape == (int(mask.sum()),)
+    assert np.array_equal(ep, np.nonzero(mask)[0])
+    assert np.all(np.diff(ep) >= 0)
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.sampled_from(["SB1", "SB2", "ST1", "ST2", "ST3"]), st.integers(min_value=0, max_value=2 ** 31 - 1))
+def test_convert_vector_dict_round_trip(model, seed):
+    """convert_dict picks the fitted parameters in registry order; convert_vector puts them back next to the fixed
+    ones and splits at gamma (utils.py:27-85) — for any choice of fixed parameters."""
+    from psoap_b200 import utils
+    rng = np.random.default_rng(seed)
+    names = utils.registered_params[model]
+    values = {n: float(rng.normal()) for n in names}
+    fixed = [n for n in names if rng.uniform() < 0.3]
+    p = utils.convert_dict(model, fixed, **values)
+    assert len(p) == len(names) - len(fixed)
+    p_orb, p_GP = utils.convert_vector(p, model, fixed, **values)
+    assert len(p_orb) == utils.n_params_orb[model] and len(p_orb) + len(p_GP) == len(names)
+    assert np.array_equal(np.concatenate([p_orb, p_GP]), np.array([values[n] for n in names]))
+    assert names[len(p_orb) - 1] == "gamma"
