@@ -337,7 +337,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             // Release the stage only after this warp's fragment loads have RETURNED: ptxas is free to hoist the
             // arrive above the trailing DMMAs (it has no register dependence on them), and an mbarrier arrive
             // is not ordered behind ld.shared still queued in the LSU.  fence.acq_rel.cta (MEMBAR.CTA) drains them.
-            __threadfence_block();
+            asm volatile("fence.acq_rel.cta;\n" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
