@@ -78,24 +78,57 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+CPU_SAMPLE = {"C4": 64}     # chunks of the configuration evaluated per CPU step (every 4th chunk of C4's 256)
+
+
+def workload_config(workload, n_chunks, model, world, nbranch):
+    """The `config` object of the JSON line; the reference arm prints the same keys."""
+    return {"workload": WORKLOADS[workload], "n_chunks": n_chunks, "model": model,
+            "partition": "LPT by N^3 + chain term over %d rank(s)" % world, "nbranch": nbranch,
+            "l2": "per-step working set (every chunk matrix is rebuilt and factored in place, 32-288 MB "
+                  "each) exceeds the 126 MB L2; no flush needed",
+            "collective": "one NCCL all_reduce(SUM) of the %d-entry FP64 lnlike vector" % n_chunks
+                          if world > 1 else "none (single rank)"}
+
+
+def cpu_farm(workload, steps, warmup):
+    """oracle/cpu_farm.py as a subprocess (never shares this process's CUDA context): the reference's CPU path on
+    all host cores, one BLAS thread per worker, chunks handed out dynamically, largest first."""
+    cmd = [sys.executable, "-m", "oracle.cpu_farm", "--config", workload, "--sample", str(CPU_SAMPLE.get(workload, 1)),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle.cpu_farm failed: " + out.stderr[-400:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_baseline_record(r):
+    return {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": sample_text(r), "workers": r["workers"], "blas_threads_per_worker": r["blas_threads_per_worker"],
+            "extrapolated": r["extrapolated"], "scale_to_full": r["scale_to_full"],
+            "seconds_per_sample_eval": r["seconds_per_sample_eval"], "cpu_seconds_full": r["cpu_seconds_full"],
+            "evals_per_s_from_cpu_seconds": r["evals_per_s_from_cpu_seconds"], "pool_efficiency": r["pool_efficiency"],
+            "fill_fraction": r["fill_fraction"], "lapack_fraction": r["lapack_fraction"],
+            "sample_N": r["sample_N"], "per_chunk_seconds": [round(x, 4) for x in r["per_chunk_seconds"]]}
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path on the host cores (oracle/cpu_farm.py as a subprocess:
-    reference Cython fill from oracle/_ref + scipy LAPACK, one worker per chunk slot, all host threads)."""
+    reference Cython fill from oracle/_ref + scipy LAPACK, all host cores).  Each step is one pass over a bounded
+    sample of the workload (C4: 64 of the 256 chunks, every 4th); value = 1 / (measured seconds per pass x the
+    sample-to-workload scale taken from the measured per-chunk seconds)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = {"C4": 16}.get(args.workload, 1)
-    cmd = [sys.executable, "-m", "oracle.cpu_farm", "--config", args.workload, "--sample", str(sample), "--steps",
-           str(args.steps), "--warmup", str(args.warmup)]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
-    r = json.loads(out)
+    r = cpu_farm(args.workload, args.steps, args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["evals_per_s"], "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["evals_per_s"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]},
-        "cpu_baseline": {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": sample_text(r)},
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds_per_sample_eval"], "ms_per_full_evaluation": 1e3 / r["evals_per_s"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, r["n_chunks"], r["model"], world, args.nbranch),
+        "cpu_baseline": cpu_baseline_record(r),
         "e2e": {"value": r["evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -103,11 +136,17 @@ def run_reference(args):
 
 
 def sample_text(r):
-    return ("%d of %d chunks (indices %s, N=%s) evaluated by %d worker processes x %d BLAS threads "
-            "(reference Cython fill + scipy LAPACK, python glue restated in oracle/oracle.py), %.2f s per sample "
-            "evaluation, scaled to the full workload by sum(N^3) (x%.2f)"
-            % (len(r["sample_chunks"]), r["n_chunks"], r["sample_chunks"], r["sample_N"], r["workers"],
-               r["blas_threads_per_worker"], r["seconds_per_sample_eval"], r["scale_to_full"]))
+    if not r["extrapolated"]:
+        return ("all %d chunks evaluated by %d worker processes x %d BLAS thread(s) (reference Cython fill + scipy "
+                "LAPACK, python glue restated in oracle/oracle.py), dynamic pool, %.2f s per evaluation"
+                % (r["n_chunks"], r["workers"], r["blas_threads_per_worker"], r["seconds_per_sample_eval"]))
+    return ("%d of %d chunks (every %dth, N=%d..%d) evaluated by %d worker processes x %d BLAS thread(s) (reference "
+            "Cython fill + scipy LAPACK, python glue restated in oracle/oracle.py), dynamic pool largest first, "
+            "%.2f s per sample pass (pool efficiency %.2f), scaled to the full workload by the measured per-chunk "
+            "seconds interpolated in N (x%.2f)"
+            % (len(r["sample_chunks"]), r["n_chunks"], max(1, r["n_chunks"] // len(r["sample_chunks"])),
+               min(r["sample_N"]), max(r["sample_N"]), r["workers"], r["blas_threads_per_worker"],
+               r["seconds_per_sample_eval"], r["pool_efficiency"], r["scale_to_full"]))
 
 
 def main():
@@ -128,23 +167,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     # CPU baseline first (rank 0, N=1 only), as its own process, before this process touches CUDA
-    cpu_baseline = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        sample = {"C4": 16}.get(args.workload, 1)
-        if args.workload == "C5":
-            cpu_baseline = None
-        else:
-            # bounded sample: 16 of the 256 chunks (one per host core on a 16-core box), 1 warm-up + 3 timed passes
-            out = subprocess.run([sys.executable, "-m", "oracle.cpu_farm", "--config", args.workload, "--sample",
-                                  str(sample), "--steps", "3", "--warmup", "1"], cwd=ROOT, capture_output=True,
-                                 text=True)
-            if out.returncode == 0:
-                r = json.loads(out.stdout.strip().splitlines()[-1])
-                cpu_baseline = {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
-                                "sample": sample_text(r)}
-            else:
-                cpu_baseline = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "failed: " + out.stderr[-300:]}
+    cpu_baseline, cpu_run = None, None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and args.workload != "C5":
+        try:
+            # bounded sample (C4: 64 of the 256 chunks), 1 warm-up pass + 2 timed passes
+            cpu_run = cpu_farm(args.workload, 2, 1)
+            cpu_baseline = cpu_baseline_record(cpu_run)
+        except Exception as exc:  # report, do not hide
+            cpu_baseline = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "failed: " + str(exc)[-300:]}
 
     import torch
     import torch.distributed as dist
@@ -204,6 +235,40 @@ def main():
     value = args.steps / (ms_total * 1e-3)
     lnl_check = float(np.sum(farm.chunk_lnlikes_device(p_dev[-1]).cpu().numpy()))
 
+    # ---- parity, asserted in the same run: the chunks the CPU arm sampled, same parameter vector ----------
+    parity = None
+    if cpu_run is not None:
+        got = farm.chunk_lnlikes(np.asarray(cpu_run["params"])).cpu().numpy()[cpu_run["sample_chunks"]]
+        ref = np.asarray(cpu_run["lnlike_per_chunk"])
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        parity = {"n": int(len(ref)), "max_rel_err": float(rel.max()), "tol": 1e-10,
+                  "against": "reference CPU path (%s fill + scipy LAPACK) on the %d sampled chunks, per chunk"
+                             % ("oracle/_ref Cython" if cpu_run["kind"] == "reference" else "oracle C", len(ref))}
+        assert np.all(np.isfinite(ref)) and rel.max() <= 1e-10, "parity against the CPU reference failed: %r" % parity
+
+    # ---- per-rank compute time of one evaluation WITHOUT the collective (the all-reduce inside the timed region
+    #      equalises the ranks' clocks, so the imbalance cannot be read from it) --------------------------------
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for k in range(3):
+        farm.lnprob_device(p_dev[k % len(p_dev)])
+    r1.record()
+    torch.cuda.synchronize()
+    mine = torch.tensor([r0.elapsed_time(r1) / 3.0, farm.cost_of_mine()], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    rank_ms = [float(t[0].item()) for t in allr]
+    rank_cost = [float(t[1].item()) for t in allr]
+    ranks = {"ms_min": min(rank_ms), "ms_mean": float(np.mean(rank_ms)), "ms_max": max(rank_ms), "ms": rank_ms,
+             "cost_model_imbalance": max(rank_cost) / float(np.mean(rank_cost)) - 1.0,
+             "measured_imbalance": max(rank_ms) / float(np.mean(rank_ms)) - 1.0,
+             "what": "device time of one evaluation of the rank's own chunks without the all-reduce (mean of 3); "
+                     "imbalance = max / mean - 1"}
+
     # ---- end-to-end leg: host parameter vector in, host float out, chunk vectors re-uploaded from pinned
     #      host memory every step, device->host read of the per-chunk log-likelihoods every step ------------
     for k in range(2):
@@ -238,6 +303,30 @@ def main():
         tfile = os.path.join(ROOT, "profiles", "syrk_traffic.json")
         if os.path.exists(tfile):
             traffic = json.load(open(tfile)).get("dram_bytes_per_launch_m%d_k%d" % (m_syrk, k_syrk))
+        # the covariance fill alone (HBM-write / FP64-exp bound): the largest chunk of the workload
+        big = max(chunks, key=lambda c: c["N"])
+        vel_h = synthetic.host_velocities(model, p[:_lib.N_ORB[model]], big["date1D"])
+        lw_dev = [torch.from_numpy(np.ascontiguousarray(big["lwl"] - vel_h[c][big["epoch"]] / synthetic.c_kms)).cuda()
+                  for c in range(_lib.NCOMP[model])] + [None] * (3 - _lib.NCOMP[model])
+        pg = p[_lib.N_ORB[model]:]
+        amp_a, l_a = _lib.dbl_array(pg[0::2]), _lib.dbl_array(pg[1::2])
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pfile):
+            hbm_peak, hbm_src = float(json.load(open(pfile))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        fill = {"N": big["N"], "ncomp": _lib.NCOMP[model], "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src}
+        nb = float(big["N"])
+        for kind, name, nbytes in ((0, "lower", 4.0 * nb * nb), (1, "full", 8.0 * nb * nb)):
+            t_ms = ctypes.c_double()
+            _lib.check(lib.psoap_bench_fill(kind, _lib.NCOMP[model], big["N"], _lib.ptr(lw_dev[0]), _lib.ptr(lw_dev[1]),
+                                            _lib.ptr(lw_dev[2]), amp_a, l_a, 20, ctypes.byref(t_ms)))
+            gbs = nbytes / (t_ms.value * 1e-3) * 1e-9
+            fill[name] = {"us": t_ms.value * 1e3, "algorithmic_bytes": nbytes, "gbs": gbs, "frac_hbm": gbs / hbm_peak,
+                          "gexp_s": _lib.NCOMP[model] * nb * (nb - 1) / 2.0 / (t_ms.value * 1e-3) * 1e-9}
+        fill["what"] = ("lower = fill_lower_kernel, the fill the likelihood uses (column-major lower triangle, 4 N^2 "
+                        "algorithmic bytes); full = fill_full_kernel, the fill_V11_* operator surface (row-major, both "
+                        "triangles, 8 N^2 bytes); gexp_s counts ncomp N (N-1) / 2 exponentials, whether evaluated or "
+                        "known to underflow to an exact zero; mean of 20 launches, CUDA events on the launch stream")
         roofline = {"bound": "tensor", "kernel": "syrk3_kernel (tensor-map TMA + DMMA.8x8x4 rank-%d trailing update of an m=%d lower triangle)" % (k_syrk, m_syrk),
                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
@@ -250,24 +339,21 @@ def main():
                            "duration does not exist there); step_tflops_per_gpu = algorithmic flops of the timed "
                            "region (sum over chunks of N^3/3 + 2N^2) / its measured time",
                     "step_tflops_per_gpu": step_tflops, "step_frac": step_tflops / peak.value,
-                    "algorithmic_flops_per_eval": flops_total}
+                    "algorithmic_flops_per_eval": flops_total, "fill": fill}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "n_chunks": len(chunks), "model": model,
-                       "partition": "LPT by N^3 over %d rank(s)" % world, "nbranch": args.nbranch,
-                       "l2": "per-step working set (every chunk matrix is rebuilt and factored in place, 32-288 MB "
-                             "each) exceeds the 126 MB L2; no flush needed",
-                       "collective": "one NCCL all_reduce(SUM) of the %d-entry FP64 lnlike vector" % len(chunks)
-                                     if world > 1 else "none (single rank)"},
+            "config": workload_config(args.workload, len(chunks), model, world, args.nbranch),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(hb.item()),
                     "d2h_bytes_per_step": len(chunks) * 8 * world},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
+            "ranks": ranks,
             "lnlike_sum": lnl_check,
         }
         print(json.dumps(line), flush=True)

@@ -152,6 +152,20 @@ int psoap_fp64_peak_tflops(double *tflops_out);
  * lower triangle, CUDA events on the launching stream.  flops_per_launch is the algorithmic count K m (m + 1)
  * (DSYRK convention; the upper halves of the diagonal tiles are computed but not counted). Synchronous. */
 int psoap_bench_syrk(int64_t m, int K, int reps, double *avg_ms_out, double *flops_per_launch_out);
+/* The likelihood's INTERNAL fill (csrc/fill.cuh fill_lower_kernel) written into a caller-provided matrix, for the
+ * entry-wise parity tests against psoap/matrix_functions.pyx:125-144 (+ covariance.py:322, data.py:40-63).
+ * W_dev: column-major [Np, ld], Np = N rounded up to 128, ld >= Np and even; data index i lives at i + (Np - N);
+ * only the lower triangle is written (identity in the padding).  rvec_dev [Np] receives fl - mu_GP.
+ * epoch_dev/vel_dev NULL: lwl_f/g/h are already shifted per-component vectors; otherwise lwl_f is the base vector and
+ * vel_dev [ncomp, n_epochs] the velocity table, the Doppler shift being fused into the fill.  Synchronous. */
+int psoap_debug_fill_lower(int ncomp, int64_t N, const double *lwl_f_dev, const double *lwl_g_dev,
+                           const double *lwl_h_dev, const int32_t *epoch_dev, const double *vel_dev, int n_epochs,
+                           const double *fl_dev, const double *sigma_dev, const double *amp, const double *l,
+                           double mu_GP, double *W_dev, int64_t ld, double *rvec_dev, void *stream);
+/* Times a fill kernel alone on the caller's shifted device vectors: kind 0 = the internal lower-triangle fill
+ * (4 N^2 algorithmic bytes), kind 1 = the operator-surface fill_V11_* (8 N^2 bytes).  Synchronous. */
+int psoap_bench_fill(int kind, int ncomp, int64_t N, const double *lwl_f_dev, const double *lwl_g_dev,
+                     const double *lwl_h_dev, const double *amp, const double *l, int reps, double *avg_ms_out);
 /* Host-side replay of the trailing-update tile enumeration (csrc/gemm.cuh SyrkSrc::decode; no device work): the
  * (row tile r, 64-column tile jrel) of every tile of a launch over R row tiles for part 0 (all), 1 (first ncol1
  * column tiles of every row) or 2 (the rest).  Returns the tile count, -1 if cap is too small. */

@@ -19,6 +19,7 @@ import ctypes
 import os
 import subprocess
 import sys
+import time
 import types
 
 import numpy as np
@@ -258,41 +259,48 @@ def get_velocities(model, p_orb, dates):
 _FILLS = {1: "fill_V11_f", 2: "fill_V11_f_g", 3: "fill_V11_f_g_h"}
 
 
-def _lnlike(V11, lwls, fl, sigma, amps, ls, mu_GP, use_ref_fill, cho_kwargs):
+def _lnlike(V11, lwls, fl, sigma, amps, ls, mu_GP, use_ref_fill, cho_kwargs, timers=None):
+    """`timers` (measurement only): dict that receives the seconds spent in the fill and in LAPACK."""
     if any(a < 0.0 for a in amps) or any(l < 0.0 for l in ls):
         return -np.inf
     ncomp = len(lwls)
     args = list(lwls) + [x for pair in zip(amps, ls) for x in pair]
     mod = ref_matrix_functions() if use_ref_fill else None
+    t0 = time.perf_counter()
     if mod is not None:
         getattr(mod, _FILLS[ncomp])(V11, *args)
     else:
         globals()[_FILLS[ncomp]](V11, *args)
     V11[np.diag_indices_from(V11)] += sigma ** 2
+    t1 = time.perf_counter()
     try:
         factor, flag = cho_factor(V11, **cho_kwargs)
     except np.linalg.LinAlgError:
         return -np.inf
     logdet = np.sum(2 * np.log((np.diag(factor))))
-    return -0.5 * (np.dot((fl - mu_GP).T, cho_solve((factor, flag), (fl - mu_GP))) + logdet)
+    out = -0.5 * (np.dot((fl - mu_GP).T, cho_solve((factor, flag), (fl - mu_GP))) + logdet)
+    if timers is not None:
+        timers["fill"] = timers.get("fill", 0.0) + (t1 - t0)
+        timers["lapack"] = timers.get("lapack", 0.0) + (time.perf_counter() - t1)
+    return out
 
 
-def lnlike_f(V11, wl_f, fl, sigma, amp_f, l_f, mu_GP=1., use_ref_fill=False):
+def lnlike_f(V11, wl_f, fl, sigma, amp_f, l_f, mu_GP=1., use_ref_fill=False, timers=None):
     """covariance.py:299-331 (cho_factor with defaults: copy, finite check)."""
-    return _lnlike(V11, [wl_f], fl, sigma, [amp_f], [l_f], mu_GP, use_ref_fill, {})
+    return _lnlike(V11, [wl_f], fl, sigma, [amp_f], [l_f], mu_GP, use_ref_fill, {}, timers)
 
 
-def lnlike_f_g(V11, wl_f, wl_g, fl, sigma, amp_f, l_f, amp_g, l_g, mu_GP=1., use_ref_fill=False):
+def lnlike_f_g(V11, wl_f, wl_g, fl, sigma, amp_f, l_f, amp_g, l_g, mu_GP=1., use_ref_fill=False, timers=None):
     """covariance.py:333-354 (cho_factor(overwrite_a=True, lower=False, check_finite=False), :348)."""
     return _lnlike(V11, [wl_f, wl_g], fl, sigma, [amp_f, amp_g], [l_f, l_g], mu_GP, use_ref_fill,
-                   dict(overwrite_a=True, lower=False, check_finite=False))
+                   dict(overwrite_a=True, lower=False, check_finite=False), timers)
 
 
 def lnlike_f_g_h(V11, wl_f, wl_g, wl_h, fl, sigma, amp_f, l_f, amp_g, l_g, amp_h, l_h, mu_GP=1.,
-                 use_ref_fill=False):
+                 use_ref_fill=False, timers=None):
     """covariance.py:356-376."""
     return _lnlike(V11, [wl_f, wl_g, wl_h], fl, sigma, [amp_f, amp_g, amp_h], [l_f, l_g, l_h], mu_GP,
-                   use_ref_fill, {})
+                   use_ref_fill, {}, timers)
 
 
 lnlike = {"SB1": lnlike_f, "SB2": lnlike_f_g, "ST1": lnlike_f, "ST2": lnlike_f_g, "ST3": lnlike_f_g_h}  # :379
@@ -415,7 +423,7 @@ def predict_f_g_h_sum(lwl_f, lwl_g, lwl_h, fl_fgh, sigma_fgh, lwl_f_predict, lwl
 n_params_orb = {"SB1": 6, "SB2": 7, "ST1": 11, "ST2": 12, "ST3": 13}  # utils.py:14 (index of gamma + 1)
 
 
-def chunk_lnprob(model, p_full, chunk, V11=None, use_ref_fill=False):
+def chunk_lnprob(model, p_full, chunk, V11=None, use_ref_fill=False, timers=None):
     """sample_parallel.py:168-198 for one chunk.  `chunk` has lwl, fl, sigma (masked 1-D), mask, date1D.
     p_full is the full registered parameter vector (orbital then GP)."""
     p_orb, p_GP = p_full[:n_params_orb[model]], p_full[n_params_orb[model]:]
@@ -426,7 +434,7 @@ def chunk_lnprob(model, p_full, chunk, V11=None, use_ref_fill=False):
     N = len(chunk["fl"])
     if V11 is None:
         V11 = np.empty((N, N), dtype=np.float64)  # :163
-    return lnlike[model](V11, *lwls, chunk["fl"], chunk["sigma"], *p_GP, use_ref_fill=use_ref_fill)
+    return lnlike[model](V11, *lwls, chunk["fl"], chunk["sigma"], *p_GP, use_ref_fill=use_ref_fill, timers=timers)
 
 
 def farm_lnprob(model, p_full, chunks, use_ref_fill=False):

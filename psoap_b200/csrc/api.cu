@@ -879,6 +879,79 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     return PSOAP_OK;
 }
 
+// The INTERNAL fill of the likelihood (fill_lower_kernel: lower triangle of K + sigma^2 I, front padding, fused
+// Doppler shift) written into a caller-provided column-major matrix, for the entry-wise parity tests against
+// matrix_functions.pyx:125-144 and for timing.  epoch/vel null: lwl_f/g/h are the already shifted per-component
+// vectors; otherwise lwl_f is the base vector and vel [ncomp, n_epochs] the velocity table (data.py:40-63).
+int psoap_debug_fill_lower(int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h,
+                           const int32_t* epoch, const double* vel, int n_epochs, const double* fl, const double* sigma,
+                           const double* amp, const double* l, double mu_GP, double* W, int64_t ld, double* rvec,
+                           void* stream) {
+    if (ncomp < 1 || ncomp > 3 || N < 1 || !lwl_f || !fl || !sigma || !amp || !l || !W || !rvec)
+        return fail(PSOAP_ERR_ARG, "psoap_debug_fill_lower: bad arguments");
+    const int64_t Np = padded_dim(N);
+    if (ld < Np || (ld & 1) || ((uintptr_t)W & 15)) return fail(PSOAP_ERR_ARG, "psoap_debug_fill_lower: ld/alignment");
+    GpParams gp;
+    make_gp(ncomp, amp, l, &gp);
+    ZSource zs = direct_z(lwl_f, lwl_g, lwl_h);
+    if (epoch && vel) { zs.epoch = epoch; zs.vel = vel; zs.n_epochs = n_epochs; zs.shift = 1; }
+    double* scratch = nullptr;   // accumulators + info word the kernel resets
+    CUDA_TRY(cudaMalloc(&scratch, 256));
+    FactorWs ws{};
+    ws.rvec = rvec; ws.acc = scratch; ws.info = (int*)(scratch + 16); ws.Nt = Np;
+    int rc = launch_fill_lower(ncomp, (cudaStream_t)stream, W, ld, (int)(Np / NB), (int)(Np - N), zs, sigma, fl, mu_GP, gp, ws);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(scratch);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("psoap_debug_fill_lower: ") + cudaGetErrorString(e));
+    return PSOAP_OK;
+}
+
+// Times a fill kernel alone on the caller's (already Doppler-shifted, device) ln-wavelength vectors:
+// kind 0 = fill_lower_kernel (the likelihood's internal fill, column-major lower triangle, 4 N^2 algorithmic bytes),
+// kind 1 = fill_full_kernel (operator surface fill_V11_*, row-major both triangles, 8 N^2 bytes).  `reps` launches
+// between CUDA events on a private stream; the matrix is allocated here.
+int psoap_bench_fill(int kind, int ncomp, int64_t N, const double* lwl_f, const double* lwl_g, const double* lwl_h,
+                     const double* amp, const double* l, int reps, double* avg_ms_out) {
+    if (kind < 0 || kind > 1 || ncomp < 1 || ncomp > 3 || N < 1 || !lwl_f || !amp || !l || reps < 1 || !avg_ms_out)
+        return fail(PSOAP_ERR_ARG, "psoap_bench_fill: bad arguments");
+    const int64_t Np = padded_dim(N);
+    double *W = nullptr, *vec = nullptr;
+    CUDA_TRY(cudaMalloc(&W, (size_t)Np * Np * 8));
+    CUDA_TRY(cudaMalloc(&vec, (size_t)(3 * Np + 64) * 8));
+    CUDA_TRY(cudaMemset(vec, 0, (size_t)(3 * Np + 64) * 8));
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    GpParams gp;
+    make_gp(ncomp, amp, l, &gp);
+    ZSource zs = direct_z(lwl_f, lwl_g, lwl_h);
+    FactorWs ws{};
+    ws.rvec = vec; ws.acc = vec + 3 * Np; ws.info = (int*)(vec + 3 * Np + 16); ws.Nt = Np;
+    const double* sigma = vec + Np;   // zeros
+    const double* fl = vec + 2 * Np;  // zeros
+    int rc = PSOAP_OK;
+    auto launch = [&]() {
+        if (kind == 0) rc = launch_fill_lower(ncomp, st, W, Np, (int)(Np / NB), (int)(Np - N), zs, sigma, fl, 1.0, gp, ws);
+        else rc = psoap_fill_v11(ncomp, W, N, N, lwl_f, lwl_g, lwl_h, amp, l, st);
+    };
+    for (int w = 0; w < 2 && !rc; ++w) launch();
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && !rc; ++i) launch();
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    cudaFree(W); cudaFree(vec);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("psoap_bench_fill: ") + cudaGetErrorString(e));
+    *avg_ms_out = ms / reps;
+    return PSOAP_OK;
+}
+
 // Host-side replay of the trailing-update tile enumeration (no device work): writes (row, column-tile) of every
 // tile of a launch over R row tiles; returns the tile count, or -1 when `cap` is too small.
 int psoap_debug_syrk_tiles(int R, int part, int ncol1, int* rows_out, int* cols_out, int cap) {

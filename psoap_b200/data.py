@@ -44,6 +44,9 @@ def replicate_wls(lwls, velocities, mask):
     ncomp, n_epochs = vel.shape
     if isinstance(mask, torch.Tensor):
         mask = mask.cpu().numpy()
+    if np.asarray(mask).shape[0] != n_epochs:
+        # data.py:61 broadcasts velocities[i][:, None] against the mask: a row-count mismatch raises there too
+        raise ValueError("mask has %d rows but velocities holds %d epochs" % (np.asarray(mask).shape[0], n_epochs))
     ep = torch.from_numpy(epoch_index(mask)).cuda()
     N = lw.numel()
     if ep.numel() != N:

@@ -30,8 +30,17 @@ def lpt_partition(costs, nparts):
     return parts
 
 
+# Cost model of one chunk for the static partition, in units of N^3: the O(N^3) trailing updates, the O(N^2) fill and
+# panel solves, and the O(N) chain of dependent diagonal blocks (N / 128 panels, each a potrf + trsm + column update
+# that cannot use more than a few SMs).  ALPHA2 / ALPHA1 are fitted to the measured farm throughput of uniform-size
+# farms on a B200 (tools/farm_cost_fit.py, profiles/README.md "cost model"); only their ratio to the cubic term matters.
+ALPHA2 = 300.0      # t(N) ~ N^3 + ALPHA2 N^2 + ALPHA1 N
+ALPHA1 = 0.0
+
+
 def chunk_cost(N):
-    return float(N) ** 3
+    n = float(N)
+    return n ** 3 + ALPHA2 * n * n + ALPHA1 * n
 
 
 class ChunkFarm:
@@ -54,6 +63,7 @@ class ChunkFarm:
         # a chunk whose mask removed every pixel contributes -0.0 in the reference (sums over nothing): it takes no
         # device work here and its entry of the per-chunk vector stays 0
         self.mine = [i for i in sorted(self.parts[rank]) if len(chunks[i]["fl"]) > 0]
+        self._cost_mine = float(sum(chunk_cost(len(chunks[i]["fl"])) for i in self.parts[rank]))
         # every chunk vector lives in ONE pinned host buffer and ONE device buffer (256-byte aligned slices), so a
         # refresh of the resident data is a single host->device copy
         hosts, offsets, total = [], [], 0
@@ -68,6 +78,13 @@ class ChunkFarm:
             N = len(host["fl"])
             if not (len(host["lwl"]) == len(host["sigma"]) == len(host["epoch"]) == N):
                 raise ValueError("chunk %d: lwl, fl, sigma and the mask must select the same number of pixels" % idx)
+            # the device reads vel[c * n_epochs + epoch[i]]: an index outside date1D would be an out-of-bounds read
+            # (the reference raises a broadcasting error for a mask that does not match date1D, data.py:61)
+            if "mask" in ch and np.asarray(ch["mask"]).shape[0] != len(host["dates"]):
+                raise ValueError("chunk %d: the mask has %d rows but date1D has %d epochs"
+                                 % (idx, np.asarray(ch["mask"]).shape[0], len(host["dates"])))
+            if N and (host["epoch"].min() < 0 or host["epoch"].max() >= len(host["dates"])):
+                raise ValueError("chunk %d: epoch indices must lie in [0, %d)" % (idx, len(host["dates"])))
             off = {}
             for k2, v in host.items():
                 off[k2] = total
@@ -98,6 +115,7 @@ class ChunkFarm:
         self._results = torch.zeros((K, max(1, len(self.mine)), 4), dtype=torch.float64, device="cuda")
         self._p_dev = torch.zeros((K, self.n_params), dtype=torch.float64, device="cuda")
         self._p_pin = torch.zeros((K, self.n_params), dtype=torch.float64).pin_memory()
+        self._p_event = None
         self._lnl_all = torch.zeros((K, self.n_chunks), dtype=torch.float64, device="cuda")
         self._lnl_pin = torch.zeros((K, self.n_chunks), dtype=torch.float64).pin_memory()
         self._mine_idx = torch.tensor(self.mine, dtype=torch.int64, device="cuda")
@@ -112,6 +130,10 @@ class ChunkFarm:
             self.launches_per_eval = lib.psoap_farm_launches_per_eval(self._farm)
 
     # -- per-rank work --------------------------------------------------------------------------------
+    def cost_of_mine(self):
+        """This rank's load under the partition's cost model (bench.py reports max / mean over ranks)."""
+        return self._cost_mine
+
     def flops_per_eval(self):
         """Algorithmic flops of this rank's chunks: N^3/3 + 2 N^2 each."""
         return float(sum(n ** 3 / 3.0 + 2.0 * n ** 2 for n in self.Ns))
@@ -150,8 +172,14 @@ class ChunkFarm:
         if p is None:
             raise ValueError("p must hold %d x %d registered parameters of %s"
                              % (self.n_proposals, self.n_params, self.model))
+        # the previous call's asynchronous upload may still be reading the pinned staging buffer
+        if self._p_event is not None:
+            self._p_event.synchronize()
         self._p_pin.copy_(torch.from_numpy(np.ascontiguousarray(p)))
         self._p_dev.copy_(self._p_pin, non_blocking=True)
+        if self._p_event is None:
+            self._p_event = torch.cuda.Event()
+        self._p_event.record()
         return self.chunk_lnlikes_device(self._p_dev)
 
     def _allreduce(self, t):

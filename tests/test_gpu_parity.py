@@ -352,6 +352,115 @@ def test_full_size_configs(cfg, oracle, torch_cuda):
     assert rel_close(got_p, got, LNLIKE_RTOL), (got_p, got)
 
 
+def _reference_cpu_lnprob(oracle, model, p, ch):
+    """The reference's CPU path for one chunk (sample_parallel.py:168-198): fsolve orbits, numpy Doppler shift, the
+    reference's own compiled Cython fill when oracle/_ref holds it (C restatement otherwise), scipy cho_factor/solve."""
+    return oracle.chunk_lnprob(model, p, ch, use_ref_fill=True)
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
+def test_full_size_vs_reference_cpu(cfg, oracle, torch_cuda):
+    """BASELINE.json configs C1-C3 at FULL size against the reference CPU path (matrix_functions.pyx fill +
+    scipy LAPACK, covariance.py:299-376), through the operator surface and through the ChunkFarm (device orbit
+    solve + fused Doppler shift): 1e-10 relative on lnlike."""
+    from psoap_b200 import covariance, synthetic
+    from psoap_b200.farm import ChunkFarm
+    model, chunks = synthetic.config_chunks(cfg)
+    ch = chunks[0]
+    p = synthetic.default_params(model)
+    ref = _reference_cpu_lnprob(oracle, model, p, ch)
+    vel = oracle.get_velocities(model, p[:N_ORB[model]], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    got = covariance.lnlike[model](None, *lwls, ch["fl"], ch["sigma"], *p[N_ORB[model]:])
+    assert np.isfinite(ref) and rel_close(got, ref, LNLIKE_RTOL), (cfg, got, ref)
+    farm = ChunkFarm(model, chunks)
+    got_farm = farm.lnprob(p)
+    farm.close()
+    assert rel_close(got_farm, ref, LNLIKE_RTOL), (cfg, got_farm, ref)
+
+
+def test_c4_chunks_vs_reference_cpu(oracle, torch_cuda):
+    """Four chunks of the bench workload C4 (N = 2000, 3320, 4660, 6000: the smallest, two interior and the largest)
+    through the ChunkFarm against the reference CPU path, per chunk."""
+    from psoap_b200 import synthetic
+    from psoap_b200.farm import ChunkFarm
+    model, chunks = synthetic.config_chunks("C4")
+    pick = [chunks[i] for i in (0, 85, 170, 255)]
+    assert [c["N"] for c in pick] == [2000, 3320, 4660, 6000]
+    p = synthetic.default_params(model)
+    farm = ChunkFarm(model, pick, nbranch=4)
+    got = farm.chunk_lnlikes(p).cpu().numpy().copy()
+    farm.close()
+    ref = np.array([_reference_cpu_lnprob(oracle, model, p, c) for c in pick])
+    assert rel_close(got, ref, LNLIKE_RTOL), (got, ref)
+
+
+def test_package_default_hyperparameters_large(oracle, torch_cuda):
+    """amp = 0.5, l = 5 km/s for every component (the package defaults, psoap/data/config.SB2.yaml:29-32): a
+    signal-to-noise (amp/sigma)^2 some 25-100x above the other tests', i.e. the worst conditioning the explicit
+    inverse of the 128 x 128 diagonal blocks sees.  N = 4000 (SB2) and N = 4200 (ST3) against the reference CPU path."""
+    from psoap_b200 import covariance, synthetic
+    for model, ne, npx in (("SB2", 20, 200), ("ST3", 20, 210)):
+        ch = synthetic.make_chunk(model, ne, npx, seed=77)
+        p = synthetic.default_params(model)
+        p[N_ORB[model]:] = [0.5, 5.0] * synthetic.NCOMP[model]
+        ref = _reference_cpu_lnprob(oracle, model, p, ch)
+        vel = oracle.get_velocities(model, p[:N_ORB[model]], ch["date1D"])
+        lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+        got = covariance.lnlike[model](None, *lwls, ch["fl"], ch["sigma"], *p[N_ORB[model]:])
+        assert np.isfinite(ref) and rel_close(got, ref, LNLIKE_RTOL), (model, got, ref)
+
+
+@pytest.mark.parametrize("model,n_epochs,n_pix,mask_frac", [("SB1", 3, 100, 0.0), ("SB2", 5, 200, 0.01),
+                                                            ("ST3", 7, 184, 0.0), ("SB2", 20, 128, 0.0),
+                                                            ("SB2", 1, 5, 0.0)])
+def test_fill_lower_entrywise_vs_reference(model, n_epochs, n_pix, mask_frac, oracle, torch_cuda):
+    """The fill the likelihood ACTUALLY uses (fill_lower_kernel: lower triangle, front padding, interior-tile fast
+    path, Doppler shift fused from the base ln-wavelengths + epoch index + velocity table) entry by entry against
+    matrix_functions.pyx:125-144 on data.py:40-63's shifted vectors plus covariance.py:322's sigma^2 diagonal:
+    |delta| <= 1e-12 |ref| + 1e-300.  Covers pad != 0 (N = 300, 995, 1288, 5) and pad == 0 (N = 2560)."""
+    from psoap_b200 import _lib, synthetic
+    t = torch_cuda
+    lib = _lib.load()
+    ch = synthetic.make_chunk(model, n_epochs, n_pix, seed=n_pix + n_epochs, mask_frac=mask_frac)
+    N, ncomp = ch["N"], synthetic.NCOMP[model]
+    p = synthetic.default_params(model)
+    vel = oracle.get_velocities(model, p[:N_ORB[model]], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    pg = p[N_ORB[model]:]
+    ref = np.empty((N, N))
+    mf = oracle.ref_matrix_functions() or oracle
+    {1: mf.fill_V11_f, 2: mf.fill_V11_f_g, 3: mf.fill_V11_f_g_h}[ncomp](ref, *lwls, *pg)
+    ref[np.diag_indices_from(ref)] += ch["sigma"] ** 2
+    Np = (N + 127) // 128 * 128
+    pad = Np - N
+    amp, l = _lib.dbl_array(pg[0::2]), _lib.dbl_array(pg[1::2])
+    fl, sg = t.from_numpy(ch["fl"]).cuda(), t.from_numpy(ch["sigma"]).cuda()
+    for fused in (True, False):
+        W = t.full((Np, Np), -7.0, dtype=t.float64, device="cuda")     # column-major: W[c, r] is entry (r, c)
+        rvec = t.full((Np,), -7.0, dtype=t.float64, device="cuda")
+        if fused:
+            lw = [t.from_numpy(ch["lwl"]).cuda(), None, None]
+            ep, vd = t.from_numpy(ch["epoch"]).cuda(), t.from_numpy(np.ascontiguousarray(vel)).cuda()
+        else:
+            lw = [t.from_numpy(np.ascontiguousarray(x)).cuda() for x in lwls] + [None] * (3 - ncomp)
+            ep, vd = None, None
+        _lib.check(lib.psoap_debug_fill_lower(ncomp, N, _lib.ptr(lw[0]), _lib.ptr(lw[1]), _lib.ptr(lw[2]), _lib.ptr(ep),
+                                              _lib.ptr(vd), len(ch["date1D"]), _lib.ptr(fl), _lib.ptr(sg), amp, l, 0.9,
+                                              _lib.ptr(W), Np, _lib.ptr(rvec), _lib.stream_ptr()))
+        M = W.cpu().numpy().T                                           # M[r, c] = entry (r, c)
+        low = np.tril_indices(N)
+        got = M[pad:, pad:]
+        assert rel_close(got[low], ref[low], ENTRY_RTOL, ENTRY_FLOOR), (fused, np.abs(got[low] - ref[low]).max())
+        # identity in the front padding, nothing written above the diagonal
+        P = M[:, :pad]
+        assert np.array_equal(np.tril(P), np.tril(np.eye(Np)[:, :pad]))
+        assert np.array_equal(np.tril(M[:pad, :]), np.tril(np.eye(Np)[:pad, :]))
+        assert (M[np.triu_indices(Np, 1)] == -7.0).all()
+        r = rvec.cpu().numpy()
+        assert np.array_equal(r[pad:], ch["fl"] - 0.9) and not r[:pad].any()
+
+
 def test_block_additivity(oracle, torch_cuda):
     """Two pixel sets far apart in wavelength have exactly zero cross-covariance (exp underflow), so the joint
     log-likelihood is the sum of the parts."""
