@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/psoap_b200.h"
+#include "chain.cuh"
 #include "chol.cuh"
 #include "common.cuh"
 #include "fill.cuh"
@@ -69,7 +70,7 @@ int g_attr_status = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
-int g_potrf_version = 3;
+int g_potrf_version = 7;   // 7: potrf_diag7 + trsm7 (chain.cuh); 3: potrf_diag3 + trsm3 (explicit 128 x 128 inverse)
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
 int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
@@ -80,6 +81,8 @@ int set_kernel_attributes() {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF5_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF7_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -122,7 +125,8 @@ constexpr int MAX_GROUP = 4;  // panels per trailing update (rank 128 * G)
 struct FactorWs {
     double* W;
     double* P[2];   // two group buffers, each column-major [Nt, 128 * MAX_GROUP] (the adjacent panels of a group)
-    double* Linv;
+    double* Linv;   // potrf_diag3: L_kk^-1;  potrf_diag7: L_kk
+    double* Xd;     // potrf_diag7: inverses of the four 32 x 32 diagonal sub-blocks of L_kk
     double* rvec;
     double* y;
     double* acc;
@@ -135,6 +139,7 @@ size_t factor_ws_bytes(int64_t Nt) {
     b += align_up((size_t)Nt * Nt * 8, 256);
     b += 2 * align_up((size_t)Nt * MAX_GROUP * NB * 8, 256);
     b += align_up((size_t)NB * NB * 8, 256);
+    b += align_up((size_t)4 * XD_BLOCK * 8, 256);
     b += 2 * align_up((size_t)Nt * 8, 256);
     b += align_up(8 * 8, 256);
     b += align_up(2 * 4, 256);
@@ -149,6 +154,7 @@ void carve_factor_ws(char* base, int64_t Nt, FactorWs* ws, bool with_W) {
     ws->P[0] = (double*)take((size_t)Nt * MAX_GROUP * NB * 8);
     ws->P[1] = (double*)take((size_t)Nt * MAX_GROUP * NB * 8);
     ws->Linv = (double*)take((size_t)NB * NB * 8);
+    ws->Xd = (double*)take((size_t)4 * XD_BLOCK * 8);
     ws->rvec = (double*)take((size_t)Nt * 8);
     ws->y = (double*)take((size_t)Nt * 8);
     ws->acc = (double*)take(8 * 8);
@@ -219,12 +225,22 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         else if (g_potrf_version == 5)   // blocked variant (experimental, same speed today)
             potrf_diag5_kernel<<<1, 256, POTRF5_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
                                                            ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
+        else if (g_potrf_version == 7)   // blocked: one chain warp, followers, DMMA rank-32 updates (chol.cuh)
+            launch_k(potrf_diag7_kernel, 1, P7_THREADS, POTRF7_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv,
+                     ws.Xd, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
         else
             launch_k(potrf_diag3_kernel, 1, 256, POTRF_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv, ws.rvec,
                      ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
     };
     auto trsm = [&](cudaStream_t s, int kb, int q, int col0) {
         const int R = T_total - kb - 1;
+        if (g_potrf_version == 7) {   // blocked substitution against L_kk and its 32 x 32 diagonal inverses (chain.cuh)
+            Trsm7Args a;
+            a.W = W; a.ld = ld; a.kb = kb; a.Lfac = ws.Linv; a.Xd = ws.Xd;
+            a.P = pbuf(q) + (int64_t)col0 * ldp; a.ldp = ldp; a.ntiles = 4 * R;
+            launch_k(trsm7_kernel, std::min(4 * R, g_num_sms), T7_THREADS, TRSM7_SMEM, s, ln.pdl, a);
+            return;
+        }
         TrsmSrc src;
         src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
         src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
