@@ -70,7 +70,7 @@ int g_attr_status = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
-int g_potrf_version = 7;   // 7: potrf_diag7 + trsm7 (chain.cuh); 3: potrf_diag3 + trsm3 (explicit 128 x 128 inverse)
+int g_potrf_version = 3;   // 3: potrf_diag3 + trsm3 (explicit 128 x 128 inverse); 7: potrf_diag7 + trsm7 (chain.cuh, experimental)
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
 int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
