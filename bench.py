@@ -31,6 +31,7 @@ WORKLOADS = {
     "C3": "C3: ST3 lnlike_f_g_h, 1 chunk 40 epochs x 250 px, N=10000",
     "C4": "C4: SB2 chunk farm, 256 chunks x 20 epochs, N=2000..6000 (sum N^3/3 = 6.8e12 flop)",
     "C5": "C5: SB2 lnlike_f_g, 1 chunk 64 epochs x 512 px, N=32768",
+    "C6": "C6: SB2 chunk farm at the reference's own chunk size, 512 chunks x 20 epochs x 80 px, N=1600",
 }
 
 
@@ -78,7 +79,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-CPU_SAMPLE = {"C4": 64}     # chunks of the configuration evaluated per CPU step (every 4th chunk of C4's 256)
+CPU_SAMPLE = {"C4": 64, "C6": 64}     # chunks of the configuration evaluated per CPU step (every 4th chunk of C4's 256)
 
 
 def workload_config(workload, n_chunks, model, world, nbranch):
@@ -294,8 +295,8 @@ def main():
         peak = ctypes.c_double()
         _lib.check(lib.psoap_fp64_peak_tflops(ctypes.byref(peak)))
         avg_ms, fl = ctypes.c_double(), ctypes.c_double()
-        m_syrk = 4096 if args.workload in ("C1", "C4") else 8192
-        k_syrk = 512 if args.workload in ("C4", "C5") else 256   # the rank the orchestration uses for this workload
+        m_syrk = {"C1": 4096, "C4": 4096, "C6": 1536}.get(args.workload, 8192)
+        k_syrk = 512 if args.workload in ("C4", "C5", "C6") else 256   # the rank the orchestration uses for this workload
         _lib.check(lib.psoap_bench_syrk(m_syrk, k_syrk, 20, ctypes.byref(avg_ms), ctypes.byref(fl)))
         achieved = fl.value / (avg_ms.value * 1e-3) * 1e-12
         step_tflops = flops_total * value * 1e-12 / world

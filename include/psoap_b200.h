@@ -147,7 +147,7 @@ int psoap_farm_destroy(psoap_farm *farm);
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* Register-resident DMMA.8x8x4 loop on all SMs: measured FP64 tensor-pipe peak in TFLOP/s (synchronous). */
 int psoap_fp64_peak_tflops(double *tflops_out);
-/* Times the dominant kernel (the DMMA trailing update, csrc/gemm.cuh syrk3_kernel; syrk2_kernel under PSOAP_TMAP=0)
+/* Times the dominant kernel (the DMMA trailing update, csrc/gemm.cuh syrk3_kernel)
  * alone: `reps` launches of the rank-K update (K a multiple of 128, up to 512 in the factorisation) of an m x m
  * lower triangle, CUDA events on the launching stream.  flops_per_launch is the algorithmic count K m (m + 1)
  * (DSYRK convention; the upper halves of the diagonal tiles are computed but not counted). Synchronous. */

@@ -50,7 +50,6 @@ inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
 
 // ---- 2-D tensor maps for the TMA operand loads (driver entry point fetched at run time: no -lcuda) ----------
 PFN_cuTensorMapEncodeTiled g_encode_tiled = nullptr;
-int g_use_tmap = 1;  // PSOAP_TMAP=0 falls back to per-column bulk copies
 
 // column-major FP64 matrix [rows, cols] with leading dimension ld; box = {box_rows, 16 columns}
 int make_tensor_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
@@ -78,37 +77,29 @@ int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
-        cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF5_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM7_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int dev = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         g_attr_status = (int)e;
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
-        if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = atoi(c);
+        if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
-        if (const char* c = getenv("PSOAP_TMAP")) g_use_tmap = atoi(c);
-        if (e == cudaSuccess && g_use_tmap) {
+        if (e == cudaSuccess) {
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult qres;
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
                 qres == cudaDriverEntryPointSuccess && fn)
                 g_encode_tiled = (PFN_cuTensorMapEncodeTiled)fn;
             else
-                g_use_tmap = 0;
-            cudaGetLastError();
+                e = cudaErrorNotSupported;   // the tensor-map TMA path is the only operand staging there is
         }
         if (const char* c = getenv("PSOAP_LOOKAHEAD")) g_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_PDL")) g_pdl = atoi(c);
@@ -175,17 +166,34 @@ struct Lanes {
 // while its predecessor in the stream still runs, and waits in pdl_wait() (common.cuh).  Only SMALL grids are
 // pre-staged: a waiting CTA holds its SM slot, which is free when the chain is the only work (small matrices, the
 // tail of a large one) and costly while a big trailing update wants every slot.
+// g_launch_prio: CUDA priority (0 = default, negative = more urgent) given to the kernels launched next by this host
+// thread; the farm sets it per chunk (largest chunks first), which also reaches the kernel nodes of a captured graph.
+thread_local int g_launch_prio = 0;
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, int pdl_max,
+                     Args&&... args) {
+    const bool pdl = (int)(grid.x * grid.y * grid.z) <= pdl_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (g_launch_prio != 0) {
+        at[n].id = cudaLaunchAttributePriority;
+        at[n].val.priority = g_launch_prio;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, int pdl_max,
                      Args&&... args) {
-    const bool pdl = (int)grid <= pdl_max;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    return launch_k(kernel, dim3(grid), block, smem, s, pdl_max, std::forward<Args>(args)...);
 }
 
 // Partial right-looking Cholesky of the leading T_elim block columns of a T_total-block lower matrix
@@ -201,8 +209,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
                   const int* sentinel, double* result) {
     const int64_t ldp = ws.Nt;
     CUtensorMap mapW, mapLinv, mapPa[2], mapPb[2];
-    const bool tmap = g_use_tmap != 0;
-    if (tmap) {
+    {
         const uint64_t Nt = (uint64_t)T_total * NB;
         int rcm = make_tensor_map(&mapW, W, Nt, Nt, (uint64_t)ld, SA);
         if (!rcm) rcm = make_tensor_map(&mapLinv, ws.Linv, NB, NB, NB, SB);
@@ -219,13 +226,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
     auto potrf = [&](cudaStream_t s, int kb) {
-        if (g_potrf_version == 1)
-            potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc,
-                                                         ws.info, sentinel, kb == T_elim - 1, result);
-        else if (g_potrf_version == 5)   // blocked variant (experimental, same speed today)
-            potrf_diag5_kernel<<<1, 256, POTRF5_SMEM, s>>>(W, ld, kb, pad, ws.Linv, ws.rvec, ws.y + (int64_t)kb * NB,
-                                                           ws.acc, ws.info, sentinel, kb == T_elim - 1, result);
-        else if (g_potrf_version == 7)   // blocked: one chain warp, followers, DMMA rank-32 updates (chol.cuh)
+        if (g_potrf_version == 7)   // blocked: one chain warp, DMMA followers and rank-32 updates (chain.cuh, experimental)
             launch_k(potrf_diag7_kernel, 1, P7_THREADS, POTRF7_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv,
                      ws.Xd, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
         else
@@ -244,8 +245,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         TrsmSrc src;
         src.W = W; src.ld = ld; src.kb = kb; src.kbeg = (kb == 0) ? (pad / BK) * BK : 0;
         src.Linv = ws.Linv; src.P = pbuf(q) + (int64_t)col0 * ldp; src.ldp = ldp;
-        if (tmap) launch_k(trsm3_kernel, persistent_ctas(2 * R), 256, GEMM_SMEM, s, ln.pdl, src, 2 * R, mapW, mapLinv);
-        else launch_k(trsm2_kernel, persistent_ctas(2 * R), 256, GEMM_SMEM, s, ln.pdl, src, 2 * R);
+        launch_k(trsm3_kernel, persistent_ctas(2 * R), 256, GEMM_SMEM, s, ln.pdl, src, 2 * R, mapW, mapLinv);
     };
     // update of row tiles [row0, T_total) with k range [kbeg, kend) of group buffer q; the residual blocks (if
     // ykb >= 0) apply panel ykb, whose columns start at res_col0 in the buffer
@@ -262,11 +262,8 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
         const double* yk = ws.y + (int64_t)std::max(ykb, 0) * NB;
-        if (tmap)
-            launch_k(syrk3_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
-                     mapPa[q & 1], mapPb[q & 1]);
-        else
-            launch_k(syrk2_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0);
+        launch_k(syrk3_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
+                 mapPa[q & 1], mapPb[q & 1]);
         ++g_launches;
     };
     const int ngroups = (T_elim + G - 1) / G;
@@ -316,7 +313,7 @@ template <int NCOMP>
 void launch_fill_lower_t(cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
                          const double* sigma, const double* fl, double mu, const GpParams& gp, const FactorWs& ws) {
     dim3 grid(T, T);
-    fill_lower_kernel<NCOMP><<<grid, 256, 0, st>>>(W, ld, pad, zs, sigma, fl, mu, gp, ws.rvec, ws.acc, ws.info);
+    launch_k(fill_lower_kernel<NCOMP>, grid, 256, 0, st, 0, W, ld, pad, zs, sigma, fl, mu, gp, ws.rvec, ws.acc, ws.info);
 }
 
 int launch_fill_lower(int ncomp, cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
@@ -612,6 +609,7 @@ struct psoap_farm {
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> side_events;
     std::vector<double*> item_vel;    // device velocity table of each item
+    std::vector<int> item_prio;       // CUDA launch priority of each item's kernels (larger chunk = more urgent)
     bool lookahead = false;
     bool direct = false;              // issue the kernels on every call instead of replaying the captured graph
     int launches = 0;
@@ -646,7 +644,9 @@ int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
             ln.group = f->lookahead ? 0 : 4;
             ln.pdl = pdl;
+            g_launch_prio = f->item_prio[it];
             rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, f->mu, gp, ws, f->flags + it, f->results + 4 * it);
+            g_launch_prio = 0;
             if (rc) break;
         }
         cudaEventRecord(f->events[b], sb);
@@ -753,6 +753,22 @@ int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const ps
         load[b] += n * n * n;
     }
 
+    // Launch priorities: the device has a few priority levels (0 = default .. `hi`, more negative = more urgent); the
+    // items are ranked by size and the levels dealt out evenly, largest chunks most urgent, so that the chunks with
+    // the longest chains of dependent panels get SM slots whenever they have work and the small ones fill the gaps
+    // and the drain at the end of an evaluation.
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* pe = getenv("PSOAP_FARM_PRIO");
+        const bool use = pe ? (atoi(pe) != 0) : true;
+        const int nlev = lo - hi + 1;          // hi <= lo
+        f->item_prio.assign(nitems, 0);
+        if (use && nlev > 1 && nitems > 1)
+            for (int r = 0; r < nitems; ++r)   // order[] is sorted by decreasing N
+                f->item_prio[order[r]] = hi + (int)((int64_t)r * nlev / nitems);
+    }
+
     // capture the whole evaluation into one CUDA graph
     f->streams.resize(nbranch + 1);
     f->events.resize(nbranch + 1);
@@ -839,8 +855,7 @@ int psoap_farm_destroy(psoap_farm* f) {
     return PSOAP_OK;
 }
 
-// Times the trailing-update kernel (syrk3_kernel, or syrk2_kernel under PSOAP_TMAP=0: the dominant kernel of the
-// path) alone: `reps` launches of the rank-K update (K a multiple of 128) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
+// Times the trailing-update kernel (syrk3_kernel, the dominant kernel of the path) alone: `reps` launches of the rank-K update (K a multiple of 128) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
 // stream.  flops_per_launch is the algorithmic count K * m * (m + 1) (DSYRK convention).
 int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
     if (m < NB || m % NB || reps < 1 || !avg_ms_out || K < NB || K % NB || K > 2048)
@@ -869,14 +884,11 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     src.pf_mode = g_pf_mode;
     const int nctas = persistent_ctas(ntiles);
     CUtensorMap mapPa, mapPb;
-    if (g_use_tmap) {
-        rc = make_tensor_map(&mapPa, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SA);
-        if (!rc) rc = make_tensor_map(&mapPb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SB);
-        if (rc) return rc;
-    }
+    rc = make_tensor_map(&mapPa, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SA);
+    if (!rc) rc = make_tensor_map(&mapPb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SB);
+    if (rc) return rc;
     auto launch = [&]() {
-        if (g_use_tmap) syrk3_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
-        else syrk2_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0);
+        syrk3_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
         ++g_launches;
     };
     for (int w = 0; w < 2; ++w) launch();

@@ -23,7 +23,7 @@ __device__ __forceinline__ void kahan_add(double* sum, double* comp, double x) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// potrf_diag: 256 threads, thread (ti = tid%16, tc = tid/16) owns the block-cyclic entries
+// potrf_diag3: 256 threads, thread (ti = tid%16, tc = tid/16) owns the block-cyclic entries
 // (i = ti + 16p, c = tc + 16q), p >= q, in registers.  At step j an entry with c > j still holds the
 // partially updated matrix, an entry with c < j (row i > j) holds the running right-hand side of
 // L X = I, so one rank-1 update per step advances the factorisation and the inverse together.
@@ -31,141 +31,6 @@ __device__ __forceinline__ void kahan_add(double* sum, double* comp, double x) {
 // ------------------------------------------------------------------------------------------------------
 constexpr int XS = NB + 1;
 constexpr int POTRF_SMEM = (NB * XS + 2 * NB + 2 * NB + NB + NB + 512 + 4) * 8;
-
-__global__ void __launch_bounds__(256, 1)
-potrf_diag_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, double* __restrict__ Linv,
-                  double* __restrict__ rvec, double* __restrict__ yk, double* __restrict__ acc,
-                  int* __restrict__ info, const int* __restrict__ sentinel, int is_last,
-                  double* __restrict__ result) {
-    extern __shared__ double sm[];
-    double* Xs = sm;                  // Xs[c*XS + r] = X[r][c], X = L^-1
-    double* colb = Xs + NB * XS;      // [2][NB]
-    double* rowb = colb + 2 * NB;     // [2][NB]
-    double* dval = rowb + 2 * NB;     // [NB] pivots d_j
-    double* rs = dval + NB;           // [NB] residual segment
-    double* red = rs + NB;            // [256]
-    const int tid = threadIdx.x;
-    const int ti = tid & 15, tc = tid >> 4;
-    const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
-
-    double M[8][8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            if (p < q) continue;
-            const int i = ti + 16 * p, c = tc + 16 * q;
-            M[p][q] = (i >= c) ? A[i + (int64_t)c * ld] : 0.0;
-        }
-    if (tid < NB) rs[tid] = rvec[kb * NB + tid];
-
-#pragma unroll
-    for (int jq = 0; jq < 8; ++jq) {
-        for (int jr = 0; jr < 16; ++jr) {
-            const int j = 16 * jq + jr;
-            double* cb = colb + (j & 1) * NB;
-            double* rb = rowb + (j & 1) * NB;
-            if (tc == jr) {
-#pragma unroll
-                for (int p = jq; p < 8; ++p) cb[ti + 16 * p] = M[p][jq];
-            }
-            if (ti == jr) {
-#pragma unroll
-                for (int q = 0; q <= jq; ++q) rb[tc + 16 * q] = M[jq][q];
-            }
-            __syncthreads();
-            const double d = cb[j];
-            const double inv = rsqrt(d);
-            if (tid == 0) dval[j] = d;
-            if (tid < NB) {  // row j of X = L^-1 is final
-                const int c = tid;
-                Xs[c * XS + j] = (c < j) ? rb[c] * inv : ((c == j) ? inv : 0.0);
-            }
-            double li[8];
-#pragma unroll
-            for (int p = jq; p < 8; ++p) {
-                const int i = ti + 16 * p;
-                li[p] = (i > j) ? cb[i] * inv : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = tc + 16 * q;
-                double w;
-                bool special = false;
-                if (q > jq) {
-                    w = cb[c] * inv;
-                } else if (q < jq) {
-                    w = rb[c] * inv;
-                } else {
-                    w = (c > j) ? cb[c] * inv : ((c < j) ? rb[c] * inv : inv);
-                    special = (c == j);
-                }
-#pragma unroll
-                for (int p = (q > jq ? q : jq); p < 8; ++p) {
-                    const double base = special ? 0.0 : M[p][q];
-                    M[p][q] = fma(-li[p], w, base);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // logdet contribution and pivot check
-    double lg = 0.0;
-    int bad = 0x7fffffff;
-    if (tid < NB) {
-        const double d = dval[tid];
-        lg = log(d);  // = 2 log L_jj (covariance.py:329)
-        if (!(d > 0.0)) bad = tid;
-    }
-    red[tid] = lg;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    const double lgsum = red[0];
-    __syncthreads();
-    // y_k = X r_k, quad contribution
-    double y = 0.0;
-    if (tid < NB) {
-        for (int c = 0; c <= tid; ++c) y = fma(Xs[c * XS + tid], rs[c], y);
-        yk[tid] = y;
-    }
-    red[tid] = y * y;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    const double qsum = red[0];
-    // first failing pivot in this block
-    __syncthreads();
-    int* redi = reinterpret_cast<int*>(red);
-    redi[tid] = bad;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) redi[tid] = min(redi[tid], redi[tid + s]);
-        __syncthreads();
-    }
-    // L_kk^-1 for the TRSM (column-major 128x128, zeros above the diagonal)
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e & (NB - 1), c = e >> 7;
-        Linv[e] = (r >= c) ? Xs[c * XS + r] : 0.0;
-    }
-    if (tid == 0) {
-        if (redi[0] != 0x7fffffff && info[0] == 0) info[0] = kb * NB + redi[0] - pad + 1;
-        kahan_add(&acc[0], &acc[1], lgsum);
-        kahan_add(&acc[2], &acc[3], qsum);
-        if (is_last) {
-            const int inf = info[0];
-            const bool flagged = (inf != 0) || (sentinel != nullptr && sentinel[0] != 0);
-            result[0] = flagged ? -CUDART_INF : -0.5 * (acc[2] + acc[0]);  // covariance.py:331
-            result[1] = acc[0];
-            result[2] = acc[2];
-            result[3] = (double)inf;
-        }
-    }
-}
 
 // Common tail of the diagonal-block kernels: logdet and pivot check, y_k = X r_k and its norm, L_kk^-1 to
 // global memory, Kahan accumulation across panels, and the final result record on the last panel.
@@ -231,8 +96,8 @@ __device__ __forceinline__ void potrf_epilogue(int tid, int kb, int pad, const d
 }
 
 // ------------------------------------------------------------------------------------------------------
-// potrf_diag3: same algorithm and register layout as potrf_diag, with the per-step instruction count cut down
-// (the step is issue bound: 8 warps x ~130 instructions on one SM).  The owners of column j scale it BEFORE
+// The per-step instruction count is what bounds this kernel (the step is issue bound: 8 warps x ~130 instructions on
+// one SM), so the owners of column j scale it BEFORE
 // publishing (the pivot travels to them by warp shuffle, they sit in one half-warp), rows that are already
 // finished are published as zeros, so a consumer's step is 16 shared loads, <= 36 DFMA and a handful of
 // multiplies for the inverse part; no thread but the 16 column owners evaluates the reciprocal square root.
@@ -342,162 +207,6 @@ potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     potrf3_block_steps<5>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
     potrf3_block_steps<6>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
     potrf3_block_steps<7>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
-    __syncthreads();
-    potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// potrf_diag5: the same contract as potrf_diag, blocked by 16 columns so that only ONE warp walks the chain of
-// dependent pivots and the other updates are rank-16.  The matrix stays in registers in the block-cyclic layout
-// of potrf_diag (thread (ti, tc) owns rows ti+16p, columns tc+16q); entries left of the current block hold the
-// running right-hand side of L X = I (X = L^-1), so factor and inverse still advance together.  Per block b:
-//   extract : block column b (rows below), block row b (columns left) and the 16x16 diagonal block go to shared
-//             memory, one vector of 16 per matrix index idx: V[k][idx]
-//   phase A : warp 0 factors the diagonal block in registers.  Lane r holds row r; the update uses the unscaled
-//             column and the reciprocal of the pivot (LDL^T form), so a step is shuffle -> reciprocal -> multiply
-//             -> FMA and the square roots are taken once at the end, off the chain
-//   phase B : 128 threads, one per idx, solve L_bb y = V[:, idx] by forward substitution.  For idx below the
-//             block that is the scaled panel row L[idx, b]; for idx left of / inside the block it is column idx
-//             of block row b of X (the identity supplies the right-hand side inside the block)
-//   phase C : M[i][c] -= sum_k Y[k][i] Y[k][c] for every row i below the block and every c <= i: trailing matrix
-//             for c right of the block, right-hand side for c left of it (the panel's own columns restart from 0)
-// ------------------------------------------------------------------------------------------------------
-#ifdef PSOAP_POTRF_TRACE
-__device__ long long g_potrf5_trace[8][8][8];   // [warp][block][phase] clock64 stamps (lab builds only)
-#define PSOAP_TRACE5(ph) do { if ((tid & 31) == 0) g_potrf5_trace[tid >> 5][B][ph] = clock64(); } while (0)
-#else
-#define PSOAP_TRACE5(ph) do { } while (0)
-#endif
-constexpr int VS = NB + 1;
-constexpr int POTRF5_SMEM = (NB * XS + 2 * 16 * VS + 2 * 16 * 17 + 16 + NB + NB + 512) * 8;
-
-// Phase A, one warp (both half-warps run the same rows; lanes 0..15 store).  Lane r keeps row r of the block
-// ROTATED: at step j, m[t] is entry (r, j+t), so the loop body is the same code for every j (the whole kernel is
-// executed once per launch, straight-line code would be bound by instruction fetch).
-__device__ __noinline__ void potrf5_phase_a(const double* __restrict__ D, double* __restrict__ Ld,
-                                            double* __restrict__ inv16, double* __restrict__ dvalb) {
-    const int lane = threadIdx.x & 31, r = lane & 15;
-    double m[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) m[c] = (c <= r) ? D[r * 17 + c] : 0.0;
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-        const double d = __shfl_sync(0xffffffffu, m[0], j, 16);
-        const double is = rsqrt(d);
-        double uc[16];
-#pragma unroll
-        for (int t = 1; t < 16; ++t) uc[t] = __shfl_sync(0xffffffffu, m[0], j + t, 16);
-        const double l = m[0] * is;    // L[r][j]; on the pivot lane d * d^-1/2 = sqrt(d)
-        const double my = l * is;      // m[0] / d
-        if (lane < 16 && r >= j) Ld[r * 17 + j] = l;
-        if (lane == j) { inv16[j] = is; dvalb[j] = d; }
-#pragma unroll
-        for (int t = 1; t < 16; ++t) m[t - 1] = fma(-my, uc[t], m[t]);
-        m[15] = 0.0;
-    }
-}
-
-// Phase B, 128 threads: forward substitution L_bb y = V[:, idx]; y goes to Y[:, idx] and, for idx at or left of the
-// block, into row block b of X.
-__device__ __noinline__ void potrf5_phase_b(int b, const double* __restrict__ V, double* __restrict__ Y,
-                                            double* __restrict__ Xs, const double* __restrict__ Ld,
-                                            const double* __restrict__ inv16) {
-    const int idx = threadIdx.x;
-    double a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = V[k * VS + idx];
-    const bool is_x = idx < 16 * (b + 1);
-    double* xrow = Xs + idx * XS + 16 * b;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const double y = a[j] * inv16[j];
-#pragma unroll
-        for (int k = j + 1; k < 16; ++k) a[k] = fma(-Ld[k * 17 + j], y, a[k]);
-        Y[j * VS + idx] = y;
-        if (is_x) xrow[j] = y;
-    }
-}
-
-template <int B>
-__device__ __forceinline__ void potrf5_block(double (&M)[8][8], int ti, int tc, int tid, double* Xs, double* V,
-                                             double* Y, double* D, double* Ld, double* inv16, double* dval) {
-    // ---- extract
-    PSOAP_TRACE5(0);
-#pragma unroll
-    for (int p = B + 1; p < 8; ++p) V[tc * VS + ti + 16 * p] = M[p][B];
-#pragma unroll
-    for (int q = 0; q < B; ++q) V[ti * VS + tc + 16 * q] = M[B][q];
-    V[ti * VS + 16 * B + tc] = (ti == tc) ? 1.0 : 0.0;
-    if (ti >= tc) D[ti * 17 + tc] = M[B][B];
-    PSOAP_TRACE5(1);
-    __syncthreads();
-    PSOAP_TRACE5(2);
-    if (tid < 32) potrf5_phase_a(D, Ld, inv16, dval + 16 * B);
-    PSOAP_TRACE5(3);
-    __syncthreads();
-    PSOAP_TRACE5(4);
-    if (tid < NB) potrf5_phase_b(B, V, Y, Xs, Ld, inv16);
-    PSOAP_TRACE5(5);
-    __syncthreads();
-    PSOAP_TRACE5(6);
-    // ---- phase C
-    if (B < 7) {
-#pragma unroll
-        for (int p = B + 1; p < 8; ++p) M[p][B] = 0.0;
-#pragma unroll 2
-        for (int k = 0; k < 16; ++k) {
-            double li[8], w[8];
-#pragma unroll
-            for (int p = B + 1; p < 8; ++p) li[p] = Y[k * VS + ti + 16 * p];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) w[q] = Y[k * VS + tc + 16 * q];
-#pragma unroll
-            for (int p = B + 1; p < 8; ++p)
-#pragma unroll
-                for (int q = 0; q <= p; ++q) M[p][q] = fma(-li[p], w[q], M[p][q]);
-        }
-    }
-    PSOAP_TRACE5(7);
-}
-
-__global__ void __launch_bounds__(256, 1)
-potrf_diag5_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, double* __restrict__ Linv,
-                   double* __restrict__ rvec, double* __restrict__ yk, double* __restrict__ acc,
-                   int* __restrict__ info, const int* __restrict__ sentinel, int is_last,
-                   double* __restrict__ result) {
-    extern __shared__ double sm[];
-    double* Xs = sm;                  // Xs[c*XS + r] = X[r][c], X = L^-1 (lower triangle only)
-    double* V = Xs + NB * XS;         // [16][VS]
-    double* Y = V + 16 * VS;          // [16][VS]
-    double* D = Y + 16 * VS;          // [16][17]
-    double* Ld = D + 16 * 17;         // [16][17]
-    double* inv16 = Ld + 16 * 17;     // [16]
-    double* dval = inv16 + 16;        // [NB] pivots d_j
-    double* rs = dval + NB;           // [NB] residual segment
-    double* red = rs + NB;            // [512]
-    const int tid = threadIdx.x;
-    const int ti = tid & 15, tc = tid >> 4;
-    const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
-
-    double M[8][8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            if (p < q) { M[p][q] = 0.0; continue; }
-            const int i = ti + 16 * p, c = tc + 16 * q;
-            M[p][q] = (i >= c) ? A[i + (int64_t)c * ld] : 0.0;
-        }
-    if (tid < NB) rs[tid] = rvec[kb * NB + tid];
-
-    potrf5_block<0>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<1>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<2>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<3>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<4>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<5>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<6>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
-    potrf5_block<7>(M, ti, tc, tid, Xs, V, Y, D, Ld, inv16, dval);
     __syncthreads();
     potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
 }

@@ -8,8 +8,6 @@
 //     68 rows for the 64-row operand, completing on an mbarrier with a transaction count; no thread moves operand
 //     data and there is no __syncthreads in the main loop.  The 4 extra rows of a box ARE the shared-memory row
 //     padding that makes the m8n8k4 fragment loads bank-conflict free (rows past the matrix edge arrive as zeros).
-//     (TMAP = false keeps the first staging: one 1-D cp.async.bulk, SASS UBLKCP, per matrix column segment, the
-//     48 copies of a stage spread over lane 0 of the 8 warps; 3 % slower, selected by PSOAP_TMAP=0.)
 //   * consumer release goes through a second set of mbarriers ("empty"), so warps drift freely and a stage is
 //     refilled two items after it was consumed.
 //   * CTAs are persistent (2 per SM) and the TMA pipeline runs ahead ACROSS tiles: the next tile's operands
@@ -36,7 +34,6 @@ constexpr int SA = BI + 4, SB = BJ + 4;
 constexpr int STAGE_DOUBLES = BK * SA + BK * SB;
 constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8;
 constexpr int GEMM_WARPS = 8;
-constexpr uint32_t WARP_TX_BYTES = 2 * (BI * 8) + 2 * (BJ * 8);  // one warp's share of a stage
 
 // 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG): box {rows, 16 k-columns} of a column-major matrix lands as
 // [16][rows] in shared memory; with a box of 132 (68) rows that IS the padded, bank-conflict-free stage layout, so a
@@ -165,11 +162,10 @@ __device__ __forceinline__ double flip_sign(double x) {  // integer pipe, keeps 
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
 }
 
-// MODE 0: C = acc, 1: C -= acc.  TMAP: operands staged by 2-D tensor-map TMA (one elected thread, two instructions
-// per stage) instead of per-column bulk copies spread over the warps.
-template <int MODE, bool TMAP, class Src>
+// MODE 0: C = acc, 1: C -= acc.  Operands staged by 2-D tensor-map TMA: one elected thread, two instructions per stage.
+template <int MODE, class Src>
 __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride, double* sm,
-                                                const CUtensorMap* mapA = nullptr, const CUtensorMap* mapB = nullptr) {
+                                                const CUtensorMap* mapA, const CUtensorMap* mapB) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g4 = lane >> 2, tq = lane & 3;
@@ -179,7 +175,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], TMAP ? 1 : GEMM_WARPS);
+            mbar_init(&full[s], 1);
             mbar_init(&empty[s], GEMM_WARPS);
         }
         mbar_fence_init();
@@ -198,28 +194,14 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     if (p_valid) pd = src.tile(p_tile);
     auto produce = [&]() {
         const int s = produced % STAGES;
-        if (TMAP) {
-            if (tid == 0) {
-                if (produced >= STAGES) mbar_wait(&empty[s], ((produced / STAGES) - 1) & 1);
-                double* sA = sm + s * STAGE_DOUBLES;
-                double* sB = sA + BK * SA;
-                const int k0 = pd.kbeg + p_kt * BK;
-                mbar_arrive_expect_tx(&full[s], STAGE_DOUBLES * 8);
-                tma_load_2d(sA, mapA, pd.rowA, pd.colA0 + k0, &full[s]);
-                tma_load_2d(sB, mapB, pd.rowB, pd.colB0 + k0, &full[s]);
-            }
-        } else if (lane == 0) {
+        if (tid == 0) {
             if (produced >= STAGES) mbar_wait(&empty[s], ((produced / STAGES) - 1) & 1);
             double* sA = sm + s * STAGE_DOUBLES;
             double* sB = sA + BK * SA;
             const int k0 = pd.kbeg + p_kt * BK;
-            mbar_arrive_expect_tx(&full[s], WARP_TX_BYTES);
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = 2 * warp + cc;
-                tma_bulk_load(sA + c * SA, pd.Ai + (int64_t)(k0 + c) * pd.lda, BI * 8, &full[s]);
-                tma_bulk_load(sB + c * SB, pd.Bj + (int64_t)(k0 + c) * pd.ldb, BJ * 8, &full[s]);
-            }
+            mbar_arrive_expect_tx(&full[s], STAGE_DOUBLES * 8);
+            tma_load_2d(sA, mapA, pd.rowA, pd.colA0 + k0, &full[s]);
+            tma_load_2d(sB, mapB, pd.rowB, pd.colB0 + k0, &full[s]);
         }
         ++produced;
         if (++p_kt == pd.KT) {
@@ -328,18 +310,12 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 }
 
 // Persistent launch geometry: `nctas` CTAs walk the tiles round-robin.
-__global__ void __launch_bounds__(256, 2) trsm2_kernel(TrsmSrc src, int ntiles) {
-    extern __shared__ __align__(128) double sm[];
-    pdl_trigger();   // small grid: let the trailing update become resident behind it
-    pdl_wait();
-    gemm_persistent<0, false>(src, ntiles, blockIdx.x, gridDim.x, sm);
-}
 __global__ void __launch_bounds__(256, 2)
 trsm3_kernel(TrsmSrc src, int ntiles, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapLinv) {
     extern __shared__ __align__(128) double sm[];
     pdl_trigger();   // small grid: let the trailing update become resident behind it
     pdl_wait();
-    gemm_persistent<0, true>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
+    gemm_persistent<0>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
 }
 
 // residual block: r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block (deterministic two-half sum)
@@ -361,25 +337,13 @@ __device__ __forceinline__ void syrk_residual_block(const SyrkSrc& src, const do
 // (deterministic two-half sum); they come FIRST so they are not left waiting for a slot behind the persistent
 // tile workers, blocks [nres, nres + nctas).
 __global__ void __launch_bounds__(256, 2)
-syrk2_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
-             int res_col0) {
-    extern __shared__ __align__(128) double sm[];
-    pdl_wait();
-    if ((int)blockIdx.x >= nres) {
-        gemm_persistent<1, false>(src, ntiles, (int)blockIdx.x - nres, nctas, sm);
-    } else {
-        syrk_residual_block(src, yk, rvec, res_col0, sm);
-    }
-}
-
-__global__ void __launch_bounds__(256, 2)
 syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb) {
     extern __shared__ __align__(128) double sm[];
     pdl_wait();
     if ((int)blockIdx.x >= nres) {
         // same buffer, two boxes: 132 rows for the 128-row operand, 68 rows for the 64-row one
-        gemm_persistent<1, true>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
+        gemm_persistent<1>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
     } else {
         syrk_residual_block(src, yk, rvec, res_col0, sm);
     }

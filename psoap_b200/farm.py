@@ -34,8 +34,10 @@ def lpt_partition(costs, nparts):
 # panel solves, and the O(N) chain of dependent diagonal blocks (N / 128 panels, each a potrf + trsm + column update
 # that cannot use more than a few SMs).  ALPHA2 / ALPHA1 are fitted to the measured farm throughput of uniform-size
 # farms on a B200 (tools/farm_cost_fit.py, profiles/README.md "cost model"); only their ratio to the cubic term matters.
-ALPHA2 = 300.0      # t(N) ~ N^3 + ALPHA2 N^2 + ALPHA1 N
-ALPHA1 = 0.0
+# Round-2 fit (64 equal chunks, 32 branches, N = 1600 .. 6000): t(N) = 9.96e-15 N^3 - 2.6e-13 N^2 + 1.76e-8 N seconds:
+# the quadratic term is nil, the linear one is 44 % of the cubic at N = 2000 and 5 % at N = 6000.
+ALPHA2 = 0.0        # t(N) ~ N^3 + ALPHA2 N^2 + ALPHA1 N
+ALPHA1 = 1.77e6
 
 
 def chunk_cost(N):

@@ -127,4 +127,6 @@ def config_chunks(name):
                        for i in range(256)]
     if name == "C5":
         return "SB2", [make_chunk("SB2", 64, 512, seed=5)]
+    if name == "C6":   # the reference's own chunk size: 20 epochs x 80 px (scripts/psoap_generate_chunks.py:8-9), many chunks
+        return "SB2", [make_chunk("SB2", 20, 80, seed=6000 + i, wl0=5000.0 + 1.5 * i) for i in range(512)]
     raise KeyError(name)

@@ -608,13 +608,15 @@ def test_farm_many_proposals(oracle, torch_cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"PSOAP_TMAP": "0"}, {"PSOAP_POTRF": "5"}, {"PSOAP_POTRF": "1", "PSOAP_GROUP": "2"},
-                                 {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"}],
-                         ids=["per-column-tma", "blocked-potrf", "first-potrf", "no-pdl-no-lookahead", "pdl-everywhere"])
+@pytest.mark.parametrize("env", [{"PSOAP_POTRF": "7"}, {"PSOAP_POTRF": "7", "PSOAP_GROUP": "2"},
+                                 {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"},
+                                 {"PSOAP_FARM_PRIO": "0"}],
+                         ids=["blocked-chain", "blocked-chain-group2", "no-pdl-no-lookahead", "pdl-everywhere",
+                              "farm-without-priorities"])
 def test_alternative_kernel_paths(env, torch_cuda):
-    """The library's environment switches select alternative kernels for the same contract (the per-column bulk-copy
-    GEMM staging, the blocked diagonal factorisation, the first diagonal kernel).  They are read once at load time,
-    so the parity tests are re-run in a child process for each."""
+    """The library's environment switches select alternative kernels / launch modes for the same contract (the blocked
+    diagonal factorisation + blocked panel solve of csrc/chain.cuh, launch attributes).  They are read once at load
+    time, so the parity tests are re-run in a child process for each."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child_env = dict(os.environ, **env)
