@@ -123,6 +123,29 @@ int psoap_schur(double *S_dev, int64_t ld, int64_t n, int64_t m, void *workspace
 int psoap_schur_views(void *workspace_dev, int64_t n, int64_t m, double **rvec_dev, double **acc_dev,
                       int **info_dev);
 
+/* The whole prediction as ONE call (psoap/covariance.py: predict_f :25-54, predict_f_g :81-148, predict_f_g_sum :151-187,
+ * predict_f_g_h :190-251, predict_f_g_h_sum :253-297): builds the bordered matrix on the device (lower triangle only,
+ * no N^2 memset), eliminates the data block with the likelihood's kernels and reads the Schur complement out.
+ *   mode 0: components stacked, M = ncomp * m outputs: A = blockdiag(K_c(predict_c)), C = [K_c(predict_c, data_c)]_c
+ *   mode 1: summed process, M = m:                     A = sum_c K_c(predict_c) + nugget I, C = sum_c K_c(predict_c, data_c)
+ *   mode 2: as 1 with the cross block transposed (the mean of predict_f_g_h_sum multiplies by V12.T, :294); needs m == n
+ * lwl_data / lwl_predict: HOST arrays of ncomp device pointers ([n] / [m] each); amp, l: HOST arrays of ncomp doubles.
+ * delta_out_dev [M]      = C K^-1 (fl - resid_mu)   (the caller adds its mean: mu_f/mu_g..., the reference's hard-coded
+ *                          `fl - 1.0` of :140,:184,:248 is resid_mu = 1.0)
+ * Sigma_out_dev [M, M]   = A - C K^-1 C^T, row-major, both triangles; may be NULL (get_Sigma=False)
+ * result_dev             logdet / info of the data block: info != 0 is the reference's LinAlgError (:113 has no try).
+ * workspace_dev: >= psoap_predict_workspace_bytes(...) bytes, 256-byte aligned.  Asynchronous on `stream`. */
+size_t psoap_predict_workspace_bytes(int ncomp, int mode, int64_t n, int64_t m);
+int psoap_predict(int ncomp, int mode, int64_t n, int64_t m, const double *const *lwl_data_dev, const double *fl_dev,
+                  const double *sigma_dev, const double *const *lwl_predict_dev, const double *amp, const double *l,
+                  double resid_mu, double nugget, double *delta_out_dev, double *Sigma_out_dev, void *workspace_dev,
+                  size_t workspace_bytes, psoap_result *result_dev, void *stream);
+/* Same with HOST vectors in and HOST delta / Sigma / result out (synchronous; device memory is allocated and freed
+ * inside): the entry a C caller without device buffers binds. */
+int psoap_predict_host(int ncomp, int mode, int64_t n, int64_t m, const double *const *lwl_data, const double *fl,
+                       const double *sigma, const double *const *lwl_predict, const double *amp, const double *l,
+                       double resid_mu, double nugget, double *delta_out, double *Sigma_out, psoap_result *result);
+
 /* ---- chunk farm: psoap/sample_parallel.py:168-198, :371-390 ------------------------------------------ */
 typedef struct psoap_farm psoap_farm;
 size_t psoap_farm_workspace_bytes(int nchunks, const int64_t *N, const int32_t *n_epochs, int nbranch);

@@ -57,6 +57,14 @@ SIGNATURES = {
     "psoap_schur": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_size_t, vp, vp]),
     "psoap_schur_views": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                          ctypes.POINTER(vp)]),
+    "psoap_predict_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64]),
+    "psoap_predict": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(vp), vp,
+                                     vp, ctypes.POINTER(vp), c_double_p, c_double_p, ctypes.c_double, ctypes.c_double,
+                                     vp, vp, vp, ctypes.c_size_t, vp, vp]),
+    "psoap_predict_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.POINTER(c_double_p), c_double_p, c_double_p,
+                                          ctypes.POINTER(c_double_p), c_double_p, c_double_p, ctypes.c_double,
+                                          ctypes.c_double, c_double_p, c_double_p, ctypes.POINTER(PsoapResult)]),
     "psoap_farm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, c_i64_p, c_i32_p, ctypes.c_int]),
     "psoap_farm_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.POINTER(PsoapChunk),
                                          ctypes.c_int, ctypes.c_double, vp, ctypes.c_size_t]),

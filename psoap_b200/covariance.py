@@ -155,6 +155,31 @@ def _out(t, on_dev):
     return t if on_dev else t.cpu().numpy()
 
 
+def _predict_device(mode, lwls, fl_d, sg_d, lwls_predict, amps, ls, resid_mu, nugget=0.0, get_Sigma=True):
+    """One psoap_predict call (include/psoap_b200.h): returns (Sigma [M, M] or None, delta [M]) on the device;
+    raises LinAlgError when the data block is not positive definite, like cho_factor (covariance.py:113 has no try)."""
+    lib = _lib.load()
+    torch = _lib.torch_cuda()
+    ncomp, n, m = len(lwls), fl_d.numel(), lwls_predict[0].numel()
+    M = ncomp * m if mode == 0 else m
+    nbytes = lib.psoap_predict_workspace_bytes(ncomp, mode, n, m)
+    if nbytes == 0:
+        raise ValueError("psoap_predict: unsupported sizes (ncomp=%d mode=%d n=%d m=%d)" % (ncomp, mode, n, m))
+    ws = _lib.workspace(nbytes + 256, "predict")
+    delta = torch.empty(M, dtype=torch.float64, device="cuda")
+    Sigma = torch.empty((M, M), dtype=torch.float64, device="cuda") if get_Sigma else None
+    res = torch.empty(4, dtype=torch.float64, device="cuda")
+    dptr = (_lib.vp * ncomp)(*[_lib.vp(v.data_ptr()) for v in lwls])
+    pptr = (_lib.vp * ncomp)(*[_lib.vp(v.data_ptr()) for v in lwls_predict])
+    _lib.check(lib.psoap_predict(ncomp, mode, n, m, dptr, _lib.ptr(fl_d), _lib.ptr(sg_d), pptr, _lib.dbl_array(amps),
+                                 _lib.dbl_array(ls), float(resid_mu), float(nugget), _lib.ptr(delta), _lib.ptr(Sigma),
+                                 _lib.ptr(ws), nbytes, _lib.ptr(res), _lib.stream_ptr()))
+    info = float(res[3].item())
+    if info != 0.0:
+        raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % int(info))
+    return Sigma, delta
+
+
 def _fill_data_block(B, lwls, amps, ls, sigma_d):
     matrix_functions._fill_v11(B.data_block(), lwls, amps, ls)
     B.data_block().diagonal().add_(sigma_d * sigma_d)  # covariance.py:110 (sigma**2 on the diagonal)
@@ -168,14 +193,10 @@ def _predict_components(lwls, fl, sigma, lwls_predict, mus, amps, ls, get_Sigma=
     lw = [_lib.dev_f64(v) for v in lwls]
     lp = [_lib.dev_f64(v) for v in lwls_predict]
     fl_d, sg_d = _lib.dev_f64(fl), _lib.dev_f64(sigma)
-    n, mp = fl_d.numel(), lp[0].numel()
-    B = _Bordered(n, ncomp * mp)
-    _fill_data_block(B, lw, amps, ls, sg_d)
-    for c in range(ncomp):
-        # A = blockdiag(K_c(predict_c)); C = [K_c(predict_c, data_c)]  (covariance.py:117-136)
-        matrix_functions._fill_v11(B.border_block(c * mp, (c + 1) * mp), [lp[c]], [amps[c]], [ls[c]])
-        matrix_functions.fill_V12_sum(B.cross_block(c * mp, (c + 1) * mp), [lw[c]], [lp[c]], [amps[c]], [ls[c]])
-    Sigma, delta = B.schur(fl_d - 1.0)  # the hard-coded 1.0 of covariance.py:140,:248
+    mp = lp[0].numel()
+    # A = blockdiag(K_c(predict_c)); C = [K_c(predict_c, data_c)]  (covariance.py:117-136); the hard-coded 1.0 of
+    # covariance.py:140,:248 is the residual mean
+    Sigma, delta = _predict_device(0, lw, fl_d, sg_d, lp, amps, ls, 1.0, 0.0, get_Sigma)
     mu_cat = torch.cat([torch.full((mp,), float(m), dtype=torch.float64, device="cuda") for m in mus])
     mu = mu_cat + delta
     if get_Sigma:
@@ -212,17 +233,9 @@ def _predict_sum(lwls, fl, sigma, lwls_predict, amps, ls, nugget, resid_mu, tran
     fl_d, sg_d = _lib.dev_f64(fl), _lib.dev_f64(sigma)
     n, mp = fl_d.numel(), lp[0].numel()
 
-    def run(transposed):
-        B = _Bordered(n, mp)
-        _fill_data_block(B, lw, amps, ls, sg_d)
-        matrix_functions._fill_v11(B.border_block(0, mp), lp, amps, ls)  # V11 = sum_c K_c(predict_c)
-        if nugget:
-            B.border_block(0, mp).diagonal().add_(nugget)               # covariance.py:165
-        if transposed:   # border = V12^T: S(border a, data j) = V12[j, a] = sum_c k_c(data_c[a] - predict_c[j])
-            matrix_functions.fill_V12_sum(B.cross_block(0, mp), lp, lw, amps, ls)
-        else:            # border = V12: S(border a, data j) = sum_c k_c(data_c[j] - predict_c[a])
-            matrix_functions.fill_V12_sum(B.cross_block(0, mp), lw, lp, amps, ls)
-        return B.schur(fl_d - resid_mu)
+    def run(transposed, want_Sigma=True):
+        # V11 = sum_c K_c(predict_c) (+ nugget, covariance.py:165); border = V12, or V12^T for the quirk of :294
+        return _predict_device(2 if transposed else 1, lw, fl_d, sg_d, lp, amps, ls, resid_mu, nugget, want_Sigma)
 
     Sigma, delta = run(False)
     if transpose_mean:
@@ -230,7 +243,7 @@ def _predict_sum(lwls, fl, sigma, lwls_predict, amps, ls, nugget, resid_mu, tran
         if mp != n:
             raise ValueError("shapes (%d,%d) and (%d,) not aligned: predict_f_g_h_sum needs M == N "
                              "(covariance.py:294 uses V12.T)" % (n, mp, n))
-        _, delta = run(True)
+        _, delta = run(True, False)
     return Sigma, delta, on_dev
 
 
@@ -258,11 +271,7 @@ def predict_f(lwl_known, fl_known, sigma_known, lwl_predict, amp_f, l_f, mu_GP=1
     on_dev = _is_dev(fl_known)
     lw, lp = _lib.dev_f64(lwl_known), _lib.dev_f64(lwl_predict)
     fl_d, sg_d = _lib.dev_f64(fl_known), _lib.dev_f64(sigma_known)
-    B = _Bordered(fl_d.numel(), lp.numel())
-    _fill_data_block(B, [lw], [amp_f], [l_f], sg_d)
-    matrix_functions._fill_v11(B.border_block(0, lp.numel()), [lp], [amp_f], [l_f])
-    matrix_functions.fill_V12_sum(B.cross_block(0, lp.numel()), [lw], [lp], [amp_f], [l_f])
-    Sigma, delta = B.schur(fl_d - float(mu_GP))
+    Sigma, delta = _predict_device(0, [lw], fl_d, sg_d, [lp], [amp_f], [l_f], float(mu_GP))
     return _out(mu_GP + delta, on_dev), _out(Sigma, on_dev)
 
 

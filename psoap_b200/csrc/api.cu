@@ -20,6 +20,7 @@
 #include "fill.cuh"
 #include "gemm.cuh"
 #include "orbit.cuh"
+#include "predict.cuh"
 
 using namespace psoap;
 
@@ -312,8 +313,8 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
 template <int NCOMP>
 void launch_fill_lower_t(cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
                          const double* sigma, const double* fl, double mu, const GpParams& gp, const FactorWs& ws) {
-    dim3 grid(T, T);
-    launch_k(fill_lower_kernel<NCOMP>, grid, 256, 0, st, 0, W, ld, pad, zs, sigma, fl, mu, gp, ws.rvec, ws.acc, ws.info);
+    launch_k(fill_lower_kernel<NCOMP>, (unsigned)(T * (T + 1) / 2), 256, 0, st, 0, W, ld, pad, zs, sigma, fl, mu, gp, ws.rvec,
+             ws.acc, ws.info);
 }
 
 int launch_fill_lower(int ncomp, cudaStream_t st, double* W, int64_t ld, int T, int pad, const ZSource& zs,
@@ -407,7 +408,7 @@ int psoap_fill_v11(int ncomp, double* mat, int64_t ld, int64_t N, const double* 
     ZSource zs = direct_z(lwl_f, lwl_g, lwl_h);
     cudaStream_t st = (cudaStream_t)stream;
     const int T = (int)((N + 63) / 64);
-    dim3 grid(T, T);
+    const unsigned grid = (unsigned)((int64_t)T * (T + 1) / 2);
     if (ncomp == 1) fill_full_kernel<1><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
     else if (ncomp == 2) fill_full_kernel<2><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
     else fill_full_kernel<3><<<grid, 256, 0, st>>>(mat, ld, (int)N, zs, gp);
@@ -583,6 +584,123 @@ extern "C" int psoap_schur_views(void* workspace, int64_t n, int64_t m, double**
     if (rvec) *rvec = ws.rvec;
     if (acc) *acc = ws.acc;
     if (info) *info = ws.info;
+    return PSOAP_OK;
+}
+
+// ---- prediction as ONE entry (psoap/covariance.py:25-297) ----------------------------------------------
+namespace {
+int predict_dims(int ncomp, int mode, int64_t n, int64_t m, int64_t* M, int64_t* Nn, int64_t* Nt) {
+    if (ncomp < 1 || ncomp > 3 || mode < 0 || mode > 2 || n < 1 || m < 1 || n > 200000 || m > 200000) return 1;
+    if (mode == 2 && m != n) return 1;
+    *M = (mode == 0) ? ncomp * m : m;
+    *Nn = padded_dim(n);
+    *Nt = *Nn + padded_dim(*M);
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t psoap_predict_workspace_bytes(int ncomp, int mode, int64_t n, int64_t m) {
+    int64_t M, Nn, Nt;
+    if (predict_dims(ncomp, mode, n, m, &M, &Nn, &Nt)) return 0;
+    return align_up((size_t)Nt * Nt * 8, 256) + psoap_schur_workspace_bytes(n, M);
+}
+
+extern "C" int psoap_predict(int ncomp, int mode, int64_t n, int64_t m, const double* const* lwl_data,
+                             const double* fl, const double* sigma, const double* const* lwl_predict, const double* amp,
+                             const double* l, double resid_mu, double nugget, double* delta_out, double* Sigma_out,
+                             void* workspace, size_t workspace_bytes, psoap_result* result, void* stream) {
+    int64_t M, Nn, Nt;
+    if (predict_dims(ncomp, mode, n, m, &M, &Nn, &Nt) || !lwl_data || !fl || !sigma || !lwl_predict || !amp || !l ||
+        !delta_out || !result)
+        return fail(PSOAP_ERR_ARG, "psoap_predict: bad arguments");
+    for (int c = 0; c < ncomp; ++c)
+        if (!lwl_data[c] || !lwl_predict[c]) return fail(PSOAP_ERR_ARG, "psoap_predict: null vector");
+    if (!workspace || workspace_bytes < psoap_predict_workspace_bytes(ncomp, mode, n, m) || ((uintptr_t)workspace & 255))
+        return fail(PSOAP_ERR_WORKSPACE, "psoap_predict: workspace too small or not 256-byte aligned");
+    int rc = set_kernel_attributes();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* S = (double*)workspace;
+    FactorWs ws;
+    carve_factor_ws((char*)workspace + align_up((size_t)Nt * Nt * 8, 256), Nt, &ws, false);
+    GpParams gp;
+    make_gp(ncomp, amp, l, &gp);
+    const int pad = (int)(Nn - n);
+    // data block: the likelihood's own fill (lower triangle, front padding, residual fl - resid_mu, accumulator reset)
+    rc = launch_fill_lower(ncomp, st, S, Nt, (int)(Nn / NB), pad, direct_z(lwl_data[0], ncomp > 1 ? lwl_data[1] : nullptr,
+                                                                          ncomp > 2 ? lwl_data[2] : nullptr),
+                           sigma, fl, resid_mu, gp, ws);
+    if (rc) return rc;
+    PredictSrc ps;
+    for (int c = 0; c < 3; ++c) { ps.data[c] = c < ncomp ? lwl_data[c] : nullptr; ps.pred[c] = c < ncomp ? lwl_predict[c] : nullptr; }
+    ps.ncomp = ncomp; ps.mode = mode; ps.n = (int)n; ps.m = (int)m; ps.M = (int)M;
+    ps.pad = pad; ps.Nn = (int)Nn; ps.Nt = (int)Nt; ps.nugget = nugget;
+    const int Tn = (int)(Nn / NB), Tt = (int)(Nt / NB);
+    const unsigned ntile = (unsigned)((int64_t)Tt * (Tt + 1) / 2 - (int64_t)Tn * (Tn + 1) / 2);
+    if (ncomp == 1) predict_border_kernel<1><<<ntile, 256, 0, st>>>(S, Nt, ps, gp, ws.rvec);
+    else if (ncomp == 2) predict_border_kernel<2><<<ntile, 256, 0, st>>>(S, Nt, ps, gp, ws.rvec);
+    else predict_border_kernel<3><<<ntile, 256, 0, st>>>(S, Nt, ps, gp, ws.rvec);
+    LAUNCH_CHECK();
+    Lanes ln;
+    rc = get_lanes(st, &ln);
+    if (rc) return rc;
+    rc = launch_factor(ln, S, Nt, Tn, Tt, pad, ws, nullptr, (double*)result);
+    if (rc) return rc;
+    const unsigned nb = (unsigned)((M + 31) / 32);
+    predict_readout_kernel<<<dim3(nb, nb), 256, 0, st>>>(S, Nt, (int)Nn, (int)M, ws.rvec, Sigma_out, delta_out);
+    LAUNCH_CHECK();
+    return PSOAP_OK;
+}
+
+// Host buffers in, host buffers out (synchronous): what a C caller without device memory binds.
+extern "C" int psoap_predict_host(int ncomp, int mode, int64_t n, int64_t m, const double* const* lwl_data,
+                                  const double* fl, const double* sigma, const double* const* lwl_predict,
+                                  const double* amp, const double* l, double resid_mu, double nugget,
+                                  double* delta_out, double* Sigma_out, psoap_result* result) {
+    int64_t M, Nn, Nt;
+    if (predict_dims(ncomp, mode, n, m, &M, &Nn, &Nt) || !lwl_data || !fl || !sigma || !lwl_predict || !amp || !l ||
+        !delta_out || !result)
+        return fail(PSOAP_ERR_ARG, "psoap_predict_host: bad arguments");
+    for (int c = 0; c < ncomp; ++c)
+        if (!lwl_data[c] || !lwl_predict[c]) return fail(PSOAP_ERR_ARG, "psoap_predict_host: null vector");
+    const size_t wsb = psoap_predict_workspace_bytes(ncomp, mode, n, m);
+    const size_t vn = align_up((size_t)n * 8, 256), vm = align_up((size_t)m * 8, 256), vM = align_up((size_t)M * 8, 256);
+    const size_t sig = Sigma_out ? align_up((size_t)M * M * 8, 256) : 0;
+    const size_t total = wsb + (size_t)(ncomp + 2) * vn + (size_t)ncomp * vm + vM + sig + 512;
+    char* base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, total));
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    int rc = PSOAP_OK;
+    if (e == cudaSuccess) {
+        char* p = base + wsb;
+        auto take = [&](size_t b) { char* r = p; p += b; return (double*)r; };
+        const double *dd[3] = {nullptr, nullptr, nullptr}, *dp[3] = {nullptr, nullptr, nullptr};
+        for (int c = 0; c < ncomp && e == cudaSuccess; ++c) {
+            double* x = take(vn); dd[c] = x;
+            e = cudaMemcpyAsync(x, lwl_data[c], (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            double* y = take(vm); dp[c] = y;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(y, lwl_predict[c], (size_t)m * 8, cudaMemcpyHostToDevice, st);
+        }
+        double* dfl = take(vn); double* dsg = take(vn); double* ddelta = take(vM);
+        double* dSig = Sigma_out ? take(sig) : nullptr;
+        psoap_result* dres = (psoap_result*)take(256);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dfl, fl, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dsg, sigma, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            rc = psoap_predict(ncomp, mode, n, m, dd, dfl, dsg, dp, amp, l, resid_mu, nugget, ddelta, dSig, base, wsb, dres, st);
+        if (e == cudaSuccess && rc == PSOAP_OK) {
+            e = cudaMemcpyAsync(delta_out, ddelta, (size_t)M * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && Sigma_out) e = cudaMemcpyAsync(Sigma_out, dSig, (size_t)M * M * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(result, dres, sizeof(psoap_result), cudaMemcpyDeviceToHost, st);
+        }
+        cudaError_t e2 = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = e2;
+        cudaStreamDestroy(st);
+    }
+    cudaFree(base);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("psoap_predict_host: ") + cudaGetErrorString(e));
     return PSOAP_OK;
 }
 

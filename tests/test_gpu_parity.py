@@ -234,6 +234,72 @@ def test_predict_f_vs_oracle(oracle, torch_cuda):
     assert np.all(np.abs(mu - mu_r) <= 1e-9) and np.all(np.abs(S - S_r) <= 1e-9 * np.abs(S_r).max())
 
 
+@pytest.mark.parametrize("n_epochs,n_pix,m", [(30, 300, 600), (8, 250, 2000)], ids=["retrieve-n9000-m600", "predict-n2000-m2000"])
+def test_predict_at_script_sizes(n_epochs, n_pix, m, oracle, torch_cuda):
+    """predict_f_g at the sizes the reference's scripts use: psoap_retrieve_SB2.py:76-105 predicts each component on
+    a 2 x n_pix grid from all N = n_epochs x n_pix pixels (here N = 9000, 600 points per component: C is 1200 x 9000),
+    psoap_predict_SB2.py:75 predicts on as many points as there are data (n = m = 2000, Sigma is 4000 x 4000).
+    Tolerance: 1e-9 of the largest entry for Sigma, 1e-9 for the mean (the data are of order one)."""
+    from psoap_b200 import covariance, synthetic
+    ch = synthetic.make_chunk("SB2", n_epochs, n_pix, seed=31 + m)
+    p = synthetic.default_params("SB2")
+    vel = oracle.get_velocities("SB2", p[:7], ch["date1D"])
+    lwls = oracle.replicate_wls(ch["lwl"], vel, ch["mask"])
+    lo, hi = ch["lwl"].min() - 30.0 / oracle.c_kms, ch["lwl"].max() + 30.0 / oracle.c_kms
+    grid_f, grid_g = np.linspace(lo, hi, m), np.linspace(lo, hi, m) + 0.3 * (hi - lo) / m
+    args = (lwls[0], lwls[1], ch["fl"], ch["sigma"], grid_f, grid_g, 0.8, p[7], p[8], 0.2, p[9], p[10])
+    mu_r, S_r = oracle.predict_f_g(*args)
+    mu, S = covariance.predict_f_g(*args)
+    assert mu.shape == (2 * m,) and S.shape == (2 * m, 2 * m)
+    assert np.all(np.abs(mu - mu_r) <= 1e-9 * np.maximum(1.0, np.abs(mu_r))), np.abs(mu - mu_r).max()
+    assert np.all(np.abs(S - S_r) <= 1e-9 * np.abs(S_r).max()), np.abs(S - S_r).max()
+    assert np.array_equal(S, S.T)
+    mu_only = covariance.predict_f_g(*args, get_Sigma=False)
+    assert np.array_equal(mu_only, mu)
+
+
+def test_predict_host_entry(oracle, torch_cuda):
+    """psoap_predict_host: host arrays in, host arrays out, no Python glue between fill, elimination and read-out;
+    the three modes against the oracle's predict_f_g_h / predict_f_g_sum / predict_f_g_h_sum."""
+    from psoap_b200 import _lib, synthetic
+    lib = _lib.load()
+    ch = synthetic.make_chunk("ST3", 5, 60, seed=8)
+    p = synthetic.default_params("ST3")
+    vel = oracle.get_velocities("ST3", p[:13], ch["date1D"])
+    lwls = [np.ascontiguousarray(x) for x in oracle.replicate_wls(ch["lwl"], vel, ch["mask"])]
+    n = ch["N"]
+    amps, ls = p[13::2], p[14::2]
+
+    def call(ncomp, mode, grids, resid_mu, nugget):
+        m = len(grids[0])
+        M = ncomp * m if mode == 0 else m
+        dp = (_lib.c_double_p * ncomp)(*[x.ctypes.data_as(_lib.c_double_p) for x in lwls[:ncomp]])
+        pp = (_lib.c_double_p * ncomp)(*[g.ctypes.data_as(_lib.c_double_p) for g in grids[:ncomp]])
+        delta, Sig, res = np.empty(M), np.empty((M, M)), _lib.PsoapResult()
+        _lib.check(lib.psoap_predict_host(ncomp, mode, n, m, dp, ch["fl"].ctypes.data_as(_lib.c_double_p),
+                                          ch["sigma"].ctypes.data_as(_lib.c_double_p), pp, _lib.dbl_array(amps[:ncomp]),
+                                          _lib.dbl_array(ls[:ncomp]), resid_mu, nugget,
+                                          delta.ctypes.data_as(_lib.c_double_p), Sig.ctypes.data_as(_lib.c_double_p),
+                                          ctypes.byref(res)))
+        assert res.info == 0.0
+        return delta, Sig
+
+    def close(a, b):
+        return np.all(np.abs(a - b) <= 1e-9 * max(1.0, np.abs(b).max()))
+
+    grids = [np.ascontiguousarray(np.linspace(x.min(), x.max(), 77)) for x in lwls]
+    mu_r, S_r = oracle.predict_f_g_h(*lwls, ch["fl"], ch["sigma"], *grids, 0.5, 0.3, 0.2, *p[13:])
+    delta, Sig = call(3, 0, grids, 1.0, 0.0)
+    assert close(np.concatenate([np.full(77, v) for v in (0.5, 0.3, 0.2)]) + delta, mu_r) and close(Sig, S_r)
+    mu_r, S_r = oracle.predict_f_g_sum(lwls[0], lwls[1], ch["fl"], ch["sigma"], grids[0], grids[1], 1.0, *p[13:17])
+    delta, Sig = call(2, 1, grids, 1.0, 1e-8)
+    assert close(1.0 + delta, mu_r) and close(Sig, S_r)
+    mu_r, S_r = oracle.predict_f_g_h_sum(*lwls, ch["fl"], ch["sigma"], *lwls, 1.0, *p[13:])   # M == N quirk (covariance.py:294)
+    delta, _ = call(3, 2, lwls, 1.0, 0.0)
+    _, Sig = call(3, 1, lwls, 1.0, 0.0)
+    assert close(1.0 + delta, mu_r) and close(Sig, S_r)
+
+
 # ---------------------------------------------------------------------------------------------- farm
 def test_farm_vs_oracle(oracle, torch_cuda):
     from psoap_b200 import synthetic
