@@ -71,6 +71,11 @@ int psoap_device_count(void);
 int psoap_fill_v11(int ncomp, double *mat_dev, int64_t ld, int64_t N, const double *lwl_f_dev,
                    const double *lwl_g_dev, const double *lwl_h_dev, const double *amp, const double *l,
                    void *stream);
+/* Same for HOST arrays (mat and the ln-wavelength vectors in host memory; synchronous, the N x N result crosses PCIe):
+ * the entry a seam at matrix_functions.pyx binds, `fill_V11_f(mat, lwl_f, amp_f, l_f)` ->
+ * `psoap_fill_v11_host(1, &mat[0,0], mat.shape[1], N, &lwl_f[0], NULL, NULL, &amp_f, &l_f)`. */
+int psoap_fill_v11_host(int ncomp, double *mat, int64_t ld, int64_t N, const double *lwl_f, const double *lwl_g,
+                        const double *lwl_h, const double *amp, const double *l);
 /* fill_V12_f (:63-94): mat row-major [M, ld]; M = len(lwl_rows), N = len(lwl_cols);
  * mat[i,j] = amp^2 exp(-0.5 c^2 (lwl_cols[j] - lwl_rows[i])^2 / l^2). */
 int psoap_fill_v12(double *mat_dev, int64_t ld, int64_t M, int64_t N, const double *lwl_rows_dev,

@@ -39,6 +39,8 @@ SIGNATURES = {
     "psoap_device_count": (ctypes.c_int, []),
     "psoap_fill_v11": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int64, vp, vp, vp, c_double_p,
                                       c_double_p, vp]),
+    "psoap_fill_v11_host": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p,
+                                           c_double_p, c_double_p, c_double_p]),
     "psoap_fill_v12": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, vp, ctypes.c_double,
                                       ctypes.c_double, vp]),
     "psoap_fill_v12n": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

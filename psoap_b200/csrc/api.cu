@@ -416,6 +416,36 @@ int psoap_fill_v11(int ncomp, double* mat, int64_t ld, int64_t N, const double* 
     return PSOAP_OK;
 }
 
+// fill_V11_* for HOST arrays (synchronous): what a Cython/ctypes seam at matrix_functions.pyx binds when the caller's
+// `mat` and ln-wavelength vectors live in host memory.  The N x N result crosses PCIe; the likelihood never needs this.
+int psoap_fill_v11_host(int ncomp, double* mat, int64_t ld, int64_t N, const double* lwl_f, const double* lwl_g,
+                        const double* lwl_h, const double* amp, const double* l) {
+    if (ncomp < 1 || ncomp > 3 || !mat || !lwl_f || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h) || ld < N || N < 0 ||
+        N > (1 << 30) || !amp || !l)
+        return fail(PSOAP_ERR_ARG, "psoap_fill_v11_host: bad arguments");
+    if (N == 0) return PSOAP_OK;
+    const size_t vec = align_up((size_t)N * 8, 256);
+    char* base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, (size_t)N * N * 8 + 3 * vec));
+    double* dmat = (double*)base;
+    double* dv[3];
+    const double* hv[3] = {lwl_f, lwl_g, lwl_h};
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < 3; ++c) {
+        dv[c] = (double*)(base + (size_t)N * N * 8 + c * vec);
+        if (c < ncomp && e == cudaSuccess) e = cudaMemcpy(dv[c], hv[c], (size_t)N * 8, cudaMemcpyHostToDevice);
+    }
+    int rc = PSOAP_OK;
+    if (e == cudaSuccess)
+        rc = psoap_fill_v11(ncomp, dmat, N, N, dv[0], ncomp > 1 ? dv[1] : nullptr, ncomp > 2 ? dv[2] : nullptr, amp, l, nullptr);
+    if (e == cudaSuccess && rc == PSOAP_OK)
+        e = cudaMemcpy2D(mat, (size_t)ld * 8, dmat, (size_t)N * 8, (size_t)N * 8, (size_t)N, cudaMemcpyDeviceToHost);
+    cudaFree(base);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PSOAP_ERR_CUDA, std::string("psoap_fill_v11_host: ") + cudaGetErrorString(e));
+    return PSOAP_OK;
+}
+
 int psoap_fill_v12n(int ncomp, double* mat, int64_t ld, int64_t M, int64_t N, const double* const* rows,
                     const double* const* cols, const double* amp, const double* l, void* stream) {
     if (ncomp < 1 || ncomp > 3 || !mat || !rows || !cols || !amp || !l || ld < N || M < 0 || N < 0)

@@ -122,27 +122,58 @@ def load_chunk(fname, limit=100):
     return ch.as_farm_chunk()
 
 
-def make_lnprob(farm, model, fix_params, pars, prior=None):
-    """sample_parallel.py:371-390 with the farm in place of the worker processes."""
+def load_config(path="config.yaml"):
+    """The run's YAML configuration (sample_parallel.py:11-17; keys as in psoap/data/config.SB2.yaml)."""
+    import yaml
+    try:
+        with open(path) as f:
+            return yaml.safe_load(f)
+    except FileNotFoundError:
+        print("You need to copy a config.yaml file to this directory, and then edit the values to your particular case.")
+        raise
+
+
+def load_user_prior(directory="."):
+    """sample_parallel.py:362-369: a file `prior.py` in the run directory defining `prior(p)` (p = the SAMPLED
+    parameter vector, fixed parameters left out) overrides the default bounds-only prior.  Returns None if absent."""
+    import importlib.util
+    path = os.path.join(directory, "prior.py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("prior", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.prior
+
+
+def make_lnprob(farm, model, fix_params, pars, prior=None, user_prior=None):
+    """sample_parallel.py:371-390 with the farm in place of the worker processes.  `prior(p_orb, p_GP)` replaces the
+    default for the model; `user_prior(p)` is the reference's prior.py convention and takes precedence."""
     prior = prior or priors[model]
 
     def lnprob(p):
         p_orb, p_GP = utils.convert_vector(p, model, fix_params, **pars)
-        lnprior = prior(p_orb, p_GP)
+        lnprior = user_prior(p) if user_prior is not None else prior(p_orb, p_GP)
         if lnprior == -np.inf:
             return -np.inf
         return farm.lnprob(np.concatenate([p_orb, p_GP])) + lnprior
     return lnprob
 
 
-def run(config, chunks, run_index=0, seed=0, rank=0, world_size=1, process_group=None, verbose=True):
-    """Run the chain described by a PSOAP config dict (psoap/data/config.SB2.yaml keys: model, parameters, jumps,
-    fix_params, samples, opt_jump, outdir, soften).  Returns the sampler."""
+def run(config, chunks, run_index=0, seed=0, rank=0, world_size=1, process_group=None, verbose=True, workdir=None):
+    """Run the chain described by a PSOAP config (a dict, or the path of a config.yaml; psoap/data/config.SB2.yaml
+    keys: model, parameters, jumps, fix_params, samples, opt_jump, outdir, soften).  A `prior.py` in `workdir`
+    (default: the current directory, as in the reference) overrides the default prior.  Returns the sampler."""
     from .farm import ChunkFarm
+    if isinstance(config, str):
+        config = load_config(config)
     model, pars, fix = config["model"], config["parameters"], config["fix_params"]
+    user_prior = load_user_prior(workdir or ".")
+    if verbose and rank == 0:
+        print("Loaded user defined prior." if user_prior is not None else "Using default prior.")
     farm = ChunkFarm(model, chunks, soften=config.get("soften", 1.0), rank=rank, world_size=world_size,
                      process_group=process_group)
-    lnprob = make_lnprob(farm, model, fix, pars)
+    lnprob = make_lnprob(farm, model, fix, pars, user_prior=user_prior)
     dim = len(utils.registered_params[model]) - len(fix)
     p0 = utils.convert_dict(model, fix, **pars)
     lnp0 = lnprob(p0)

@@ -44,6 +44,14 @@ def test_fill_golden(golden, torch_cuda):
     assert rel_close(m, g["V12_f"], ENTRY_RTOL, ENTRY_FLOOR)
     m = np.empty((33, 33)); mf.fill_V11_f(m, g["far_lwl"], 0.5, 5.0)
     assert rel_close(m, g["far_V11_f"], ENTRY_RTOL, ENTRY_FLOOR)
+    # the host-buffer C entry (what a seam at matrix_functions.pyx binds), into a strided host matrix
+    from psoap_b200 import _lib
+    big = np.full((N, N + 7), -3.0)
+    vecs = [np.ascontiguousarray(lw[c]) for c in range(3)]
+    _lib.check(_lib.load().psoap_fill_v11_host(3, big.ctypes.data_as(_lib.c_double_p), N + 7, N,
+                                               *[v.ctypes.data_as(_lib.c_double_p) for v in vecs],
+                                               _lib.dbl_array(amp[:3]), _lib.dbl_array(l[:3])))
+    assert rel_close(big[:, :N], g["V11_f_g_h"], ENTRY_RTOL, ENTRY_FLOOR) and (big[:, N:] == -3.0).all()
 
 
 @pytest.mark.parametrize("N", [1, 63, 64, 65, 257, 1000])

@@ -245,3 +245,35 @@ def test_convert_vector_dict_round_trip(model, seed):
     assert len(p_orb) == utils.n_params_orb[model] and len(p_orb) + len(p_GP) == len(names)
     assert np.array_equal(np.concatenate([p_orb, p_GP]), np.array([values[n] for n in names]))
     assert names[len(p_orb) - 1] == "gamma"
+
+
+def test_yaml_config_and_user_prior_override(tmp_path):
+    """sample_parallel.py:11-17 (config.yaml) and :362-369 (a prior.py in the run directory replaces the default
+    prior): host logic only, with a stand-in for the farm."""
+    from psoap_b200 import sample, utils
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text("model: SB2\nsoften: 1.0\nsamples: 3\nfix_params: [gamma]\n"
+                   "parameters: {q: 0.2, K: 5.0, e: 0.2, omega: 10.0, P: 10.0, T0: 0.0, gamma: 5.0, amp_f: 0.1, l_f: 5.0,"
+                   " amp_g: 0.05, l_g: 7.0}\n")
+    config = sample.load_config(str(cfg))
+    assert config["model"] == "SB2" and config["parameters"]["l_g"] == 7.0 and config["fix_params"] == ["gamma"]
+    with pytest.raises(FileNotFoundError):
+        sample.load_config(str(tmp_path / "missing.yaml"))
+    assert sample.load_user_prior(str(tmp_path)) is None
+    (tmp_path / "prior.py").write_text("import numpy as np\n\ndef prior(p):\n    return -np.inf if p[1] > 6.0 else -0.5 * p[0] ** 2\n")
+    user = sample.load_user_prior(str(tmp_path))
+
+    class FakeFarm:
+        def lnprob(self, p):
+            return float(np.sum(p))
+    pars, fix = config["parameters"], config["fix_params"]
+    p0 = utils.convert_dict("SB2", fix, **pars)
+    full = np.concatenate(utils.convert_vector(p0, "SB2", fix, **pars))
+    default = sample.make_lnprob(FakeFarm(), "SB2", fix, pars)
+    custom = sample.make_lnprob(FakeFarm(), "SB2", fix, pars, user_prior=user)
+    assert default(p0) == np.sum(full)
+    assert custom(p0) == np.sum(full) - 0.5 * p0[0] ** 2
+    p1 = p0.copy(); p1[1] = 7.0
+    assert custom(p1) == -np.inf and np.isfinite(default(p1))
+    p2 = p0.copy(); p2[0] = -0.1            # q < 0: the default bounds reject it, the user prior does not
+    assert default(p2) == -np.inf and np.isfinite(custom(p2))
