@@ -109,12 +109,12 @@ int main() {
     for (int w = 0; w < 9; ++w) printf(" w%d %6lld", w, tw[b][ph][w] - base);
     printf("\n");
   }
-  static long long tf[4][8][3], tcn[4][8];
+  static long long tf[4][8][4], tcn[4][8];
   cudaMemcpyFromSymbol(tf, g_p7_fol, sizeof(tf)); cudaMemcpyFromSymbol(tcn, g_p7_chn, sizeof(tcn));
   for (int b = 0; b < 2; ++b) {
     const long long base = b ? t[1 + 2 * b] : t[1];
     printf("  block %d micro-steps (cycles since phase start): chain arrive | follower warp 1: wait-begin, wait-end, step-end\n", b);
-    for (int m = 0; m < 8; ++m) printf("    m=%d  chain %6lld | %6lld %6lld %6lld\n", m, tcn[b][m] - base, tf[b][m][0] - base, tf[b][m][1] - base, tf[b][m][2] - base);
+    for (int m = 0; m < 8; ++m) printf("    m=%d  chain %6lld | %6lld %6lld (+%lld loads) %6lld\n", m, tcn[b][m] - base, tf[b][m][0] - base, tf[b][m][1] - base, tf[b][m][3] - tf[b][m][1], tf[b][m][2] - base);
   }
   // trsm7 alone on a bigger panel: R row blocks below
   for (int Rb : {15, 37, 46}) {
