@@ -99,21 +99,20 @@ int main() {
   }
   long long t[16];
   cudaMemcpyFromSymbol(t, g_p7_trace, sizeof(t));
-  const char* names[] = {"start", "loaded", "chain0", "update0", "chain1", "update1", "chain2", "update2", "chain3", "-", "end"};
-  for (int k = 1; k <= 10; ++k) if (k != 9) printf("  %-8s +%6lld cycles (total %6lld)\n", names[k], t[k] - t[k == 10 ? 8 : k - 1], t[k] - t[0]);
+  printf("  loaded %lld | pipeline end %lld | kernel end %lld cycles\n", t[1] - t[0], t[9] - t[0], t[10] - t[0]);
   static long long tw[4][2][9];
   cudaMemcpyFromSymbol(tw, g_p7_warp, sizeof(tw));
-  for (int b = 0; b < 4; ++b) for (int ph = 0; ph < 2 && (b < 3 || ph == 0); ++ph) {
-    printf("  block %d %s: warp end times since phase start:", b, ph ? "update" : "chain ");
-    const long long base = ph ? t[2 + 2 * b] : (b ? t[1 + 2 * b] : t[1]);
-    for (int w = 0; w < 9; ++w) printf(" w%d %6lld", w, tw[b][ph][w] - base);
+  for (int b = 0; b < 4; ++b) {
+    printf("  block %d, cycles since load: chain done %6lld | store issued %6lld | followers: follow done", b, tw[b][0][0] - t[1], tw[b][0][8] - t[1]);
+    for (int w : {1, 2, 3, 5, 6, 7}) printf(" %6lld", tw[b][0][w] - t[1]);
+    if (b < 3) { printf(" | update done"); for (int w : {1, 2, 3, 5, 6, 7}) printf(" %6lld", tw[b][1][w] - t[1]); }
     printf("\n");
   }
   static long long tf[4][8][4], tcn[4][8];
   cudaMemcpyFromSymbol(tf, g_p7_fol, sizeof(tf)); cudaMemcpyFromSymbol(tcn, g_p7_chn, sizeof(tcn));
   for (int b = 0; b < 2; ++b) {
-    const long long base = b ? t[1 + 2 * b] : t[1];
-    printf("  block %d micro-steps (cycles since phase start): chain arrive | follower warp 1: wait-begin, wait-end, step-end\n", b);
+    const long long base = t[1];
+    printf("  block %d micro-steps (cycles since load): chain arrive | follower warp 1: wait-begin, wait-end, step-end\n", b);
     for (int m = 0; m < 8; ++m) printf("    m=%d  chain %6lld | %6lld %6lld (+%lld loads) %6lld\n", m, tcn[b][m] - base, tf[b][m][0] - base, tf[b][m][1] - base, tf[b][m][3] - tf[b][m][1], tf[b][m][2] - base);
   }
   // trsm7 alone on a bigger panel: R row blocks below
