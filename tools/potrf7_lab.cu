@@ -100,12 +100,12 @@ int main() {
   long long t[16];
   cudaMemcpyFromSymbol(t, g_p7_trace, sizeof(t));
   printf("  loaded %lld | pipeline end %lld | kernel end %lld cycles\n", t[1] - t[0], t[9] - t[0], t[10] - t[0]);
-  static long long tw[4][2][9];
+  static long long tw[4][2][12];
   cudaMemcpyFromSymbol(tw, g_p7_warp, sizeof(tw));
   for (int b = 0; b < 4; ++b) {
     printf("  block %d, cycles since load: chain done %6lld | store issued %6lld | followers: follow done", b, tw[b][0][0] - t[1], tw[b][0][8] - t[1]);
-    for (int w : {1, 2, 3, 5, 6, 7}) printf(" %6lld", tw[b][0][w] - t[1]);
-    if (b < 3) { printf(" | update done"); for (int w : {1, 2, 3, 5, 6, 7}) printf(" %6lld", tw[b][1][w] - t[1]); }
+    for (int w : {1, 2, 3, 5, 6, 7, 9, 10, 11}) printf(" %6lld", tw[b][0][w] - t[1]);
+    if (b < 3) { printf(" | update done"); for (int w : {1, 2, 3, 5, 6, 7, 9, 10, 11}) printf(" %6lld", tw[b][1][w] - t[1]); }
     printf("\n");
   }
   static long long tf[4][8][4], tcn[4][8];
