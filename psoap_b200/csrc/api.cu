@@ -70,7 +70,13 @@ int g_attr_status = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
 int g_yield_lookahead = 1;
-int g_potrf_version = 3;   // 3: potrf_diag3 + trsm3 (explicit 128 x 128 inverse); 7: potrf_diag7 + trsm7 (chain.cuh, experimental)
+// Chain links (diagonal block + panel solve): 7 = potrf_diag7 + trsm7 (chain.cuh: blocked factorisation with one chain
+// warp, blocked substitution), 3 = potrf_diag3 + trsm3 (explicit 128 x 128 inverse, GEMM panel solve).  7 is the faster
+// chain for a matrix factored on its own (N = 2000: 0.88 vs 1.22 ms, N = 4000: 2.11 vs 2.74 ms); inside the graph farm,
+// where chain latency is hidden by the other chunks and SM-time is what counts, 3 wins (trsm7 keeps a whole SM per
+// 32-row tile).  PSOAP_POTRF sets both, PSOAP_FARM_POTRF the farm's.
+int g_potrf_version = 7;
+int g_farm_potrf_version = 3;
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
 int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
@@ -91,7 +97,8 @@ int set_kernel_attributes() {
         g_attr_status = (int)e;
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
-        if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = (atoi(c) == 7) ? 7 : 3;
+        if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
+        if (const char* c = getenv("PSOAP_FARM_POTRF")) g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
         if (e == cudaSuccess) {
             void* fn = nullptr;
@@ -160,6 +167,7 @@ struct Lanes {
     cudaStream_t side;   // may be null: no look-ahead
     cudaEvent_t e1, e2;
     int group = 0;       // panels per trailing update (2 or 4); 0 = choose from the problem size
+    int chain = 0;       // chain links: 3 or 7; 0 = g_potrf_version
     int pdl = 0;         // grids of at most this many CTAs are launched with programmatic stream serialization (0: none)
 };
 
@@ -226,8 +234,9 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     const int G = g_group ? g_group : (ln.group ? ln.group : (T_total >= 96 ? 4 : 2));
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
+    const int chain = ln.chain ? ln.chain : g_potrf_version;
     auto potrf = [&](cudaStream_t s, int kb) {
-        if (g_potrf_version == 7)   // blocked: one chain warp, DMMA followers and rank-32 updates (chain.cuh, experimental)
+        if (chain == 7)   // blocked: one chain warp, DMMA followers and rank-32 updates (chain.cuh, experimental)
             launch_k(potrf_diag7_kernel, 1, P7_THREADS, POTRF7_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv,
                      ws.Xd, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
         else
@@ -236,7 +245,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     };
     auto trsm = [&](cudaStream_t s, int kb, int q, int col0) {
         const int R = T_total - kb - 1;
-        if (g_potrf_version == 7) {   // blocked substitution against L_kk and its 32 x 32 diagonal inverses (chain.cuh)
+        if (chain == 7) {   // blocked substitution against L_kk and its 32 x 32 diagonal inverses (chain.cuh)
             Trsm7Args a;
             a.W = W; a.ld = ld; a.kb = kb; a.Lfac = ws.Linv; a.Xd = ws.Xd;
             a.P = pbuf(q) + (int64_t)col0 * ldp; a.ldp = ldp; a.ntiles = 4 * R;
@@ -792,6 +801,7 @@ int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
             ln.group = f->lookahead ? 0 : 4;
             ln.pdl = pdl;
+            ln.chain = f->lookahead ? 0 : g_farm_potrf_version;   // fewer than 8 branches: chain latency is exposed
             g_launch_prio = f->item_prio[it];
             rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, f->mu, gp, ws, f->flags + it, f->results + 4 * it);
             g_launch_prio = 0;

@@ -682,10 +682,10 @@ def test_farm_many_proposals(oracle, torch_cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"PSOAP_POTRF": "7"}, {"PSOAP_POTRF": "7", "PSOAP_GROUP": "2"},
+@pytest.mark.parametrize("env", [{"PSOAP_POTRF": "3"}, {"PSOAP_POTRF": "7", "PSOAP_GROUP": "4"},
                                  {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"},
                                  {"PSOAP_FARM_PRIO": "0"}],
-                         ids=["blocked-chain", "blocked-chain-group2", "no-pdl-no-lookahead", "pdl-everywhere",
+                         ids=["inverse-chain-everywhere", "blocked-chain-everywhere-group4", "no-pdl-no-lookahead", "pdl-everywhere",
                               "farm-without-priorities"])
 def test_alternative_kernel_paths(env, torch_cuda):
     """The library's environment switches select alternative kernels / launch modes for the same contract (the blocked
