@@ -77,6 +77,7 @@ int g_yield_lookahead = 1;
 // 32-row tile).  PSOAP_POTRF sets both, PSOAP_FARM_POTRF the farm's.
 int g_potrf_version = 7;
 int g_farm_potrf_version = 3;
+int g_small_tiles = 1;   // PSOAP_SMALL_TILES=0: keep 128 x 64 tiles for the critical block-column updates too
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
 int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
@@ -88,9 +89,11 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<2>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int dev = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -98,6 +101,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
+        if (const char* c = getenv("PSOAP_SMALL_TILES")) g_small_tiles = atoi(c);
         if (const char* c = getenv("PSOAP_FARM_POTRF")) g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
         if (e == cudaSuccess) {
@@ -217,7 +221,7 @@ cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, si
 int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_total, int pad, const FactorWs& ws,
                   const int* sentinel, double* result) {
     const int64_t ldp = ws.Nt;
-    CUtensorMap mapW, mapLinv, mapPa[2], mapPb[2];
+    CUtensorMap mapW, mapLinv, mapPa[2], mapPb[2], mapPas[2], mapPbs[2];   // ..s: boxes of the small tile shape
     {
         const uint64_t Nt = (uint64_t)T_total * NB;
         int rcm = make_tensor_map(&mapW, W, Nt, Nt, (uint64_t)ld, SA);
@@ -225,6 +229,8 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         for (int q = 0; q < 2 && !rcm; ++q) {
             rcm = make_tensor_map(&mapPa[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SA);
             if (!rcm) rcm = make_tensor_map(&mapPb[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SB);
+            if (!rcm) rcm = make_tensor_map(&mapPas[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, Shape<2>::SA);
+            if (!rcm) rcm = make_tensor_map(&mapPbs[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, Shape<2>::SB);
         }
         if (rcm) return rcm;
     }
@@ -261,10 +267,13 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     // ykb >= 0) apply panel ykb, whose columns start at res_col0 in the buffer
     auto syrk = [&](cudaStream_t s, int q, int row0, int kend, int part, int ncol1, int ykb, int res_col0) {
         const int R = T_total - row0;
+        // part 1 (the block columns the next diagonal blocks wait for) of a matrix factored on its own: 64 x 32 tiles,
+        // four times the CTAs at a quarter of the latency each
+        const int sh = (part == 1 && chain == 7 && g_small_tiles) ? 2 : 1;
         SyrkSrc src;
-        src.W = W; src.ld = ld; src.row0 = row0; src.kbeg = kbeg_of(q); src.kend = kend;
-        src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = ncol1; src.pf_mode = g_pf_mode;
-        const int ntiles = syrk_ntiles(R, part, ncol1);
+        src.W = W; src.ld = ld; src.row0 = sh * row0; src.res_row0 = row0; src.kbeg = kbeg_of(q); src.kend = kend;
+        src.P = pbuf(q); src.ldp = ldp; src.part = part; src.ncol1 = sh * ncol1; src.pf_mode = g_pf_mode;
+        const int ntiles = syrk_ntiles(sh * R, part, sh * ncol1);
         const int nres = (part == 2 || ykb < 0) ? 0 : R;
         if (ntiles + nres == 0) return;
         // Under look-ahead the bulk update (part 2) gives up persistence: one tile per CTA, so SM slots free up
@@ -272,8 +281,12 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
         const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
         const double* yk = ws.y + (int64_t)std::max(ykb, 0) * NB;
-        launch_k(syrk3_kernel, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
-                 mapPa[q & 1], mapPb[q & 1]);
+        if (sh == 2)
+            launch_k(syrk3_kernel<2>, nctas + nres, 256, Shape<2>::SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec,
+                     res_col0, mapPas[q & 1], mapPbs[q & 1]);
+        else
+            launch_k(syrk3_kernel<1>, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
+                     mapPa[q & 1], mapPb[q & 1]);
         ++g_launches;
     };
     const int ngroups = (T_elim + G - 1) / G;
@@ -1038,7 +1051,7 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     CUDA_TRY(cudaEventCreate(&e1));
     const int R = (int)(m / NB), ntiles = R * (R + 1);
     SyrkSrc src;
-    src.W = W; src.ld = m; src.row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
+    src.W = W; src.ld = m; src.row0 = 0; src.res_row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
     src.pf_mode = g_pf_mode;
     const int nctas = persistent_ctas(ntiles);
     CUtensorMap mapPa, mapPb;
@@ -1046,7 +1059,7 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     if (!rc) rc = make_tensor_map(&mapPb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SB);
     if (rc) return rc;
     auto launch = [&]() {
-        syrk3_kernel<<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
+        syrk3_kernel<1><<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
         ++g_launches;
     };
     for (int w = 0; w < 2; ++w) launch();

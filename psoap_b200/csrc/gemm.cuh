@@ -30,10 +30,22 @@
 namespace psoap {
 
 constexpr int BI = 128, BJ = 64, BK = 16, STAGES = 4;
-constexpr int SA = BI + 4, SB = BJ + 4;
-constexpr int STAGE_DOUBLES = BK * SA + BK * SB;
-constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8;
 constexpr int GEMM_WARPS = 8;
+// Tile shapes.  SH = 1: 128 x 64 output tile (warp tile 32 x 32), the throughput shape of the trailing update.
+// SH = 2: 64 x 32 (warp tile 16 x 16), four times as many tiles of a quarter of the work each: the LATENCY shape, for
+// the short-K updates on the critical path of a matrix factored on its own (a 128 x 64 x K=128 tile keeps one SM busy
+// for 8 us at the FP64 peak; the block column it belongs to has only 2 R of them for the whole GPU).
+template <int SH>
+struct Shape {
+    static constexpr int TI = BI / SH, TJ = BJ / SH;          // tile rows (i), tile columns (j)
+    static constexpr int SA = TI + 4, SB = TJ + 4;            // padded operand rows in shared memory (= TMA box rows)
+    static constexpr int STAGE = BK * SA + BK * SB;           // doubles per pipeline stage
+    static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
+    static constexpr int NI = TI / 32, NJ = TJ / 16;          // 8 x 8 atoms per warp along i and j (warps 4 x 2)
+};
+constexpr int SA = Shape<1>::SA, SB = Shape<1>::SB;
+constexpr int STAGE_DOUBLES = Shape<1>::STAGE;
+constexpr int GEMM_SMEM = Shape<1>::SMEM;
 
 // 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG): box {rows, 16 k-columns} of a column-major matrix lands as
 // [16][rows] in shared memory; with a box of 132 (68) rows that IS the padded, bank-conflict-free stage layout, so a
@@ -71,6 +83,7 @@ struct TrsmSrc {
     const double* Linv;
     double* P;
     int64_t ldp;
+    template <int SH = 1>
     __device__ __forceinline__ TileDesc tile(int t) const {
         const int I = kb + 1 + (t >> 1), jh = t & 1;
         const int kend = (jh + 1) * BJ;
@@ -99,7 +112,8 @@ struct TrsmSrc {
 struct SyrkSrc {
     double* W;
     int64_t ld;
-    int row0, kbeg, kend;
+    int row0, kbeg, kend;   // row0 in units of the tile rows (128, or 64 for the small shape)
+    int res_row0;           // first 128-row block of the residual update
     const double* P;
     int64_t ldp;
     int part, ncol1;
@@ -131,21 +145,25 @@ struct SyrkSrc {
             r = v + (ncol1 >> 1) - 1;
         }
     }
+    // SH = 2: the same enumeration in units of 64-row / 32-column tiles (row0, R, ncol1 are then given in those units;
+    // a row tile still owns 2 r + 2 column tiles because TI = 2 TJ in both shapes)
+    template <int SH = 1>
     __device__ __forceinline__ TileDesc tile(int t) const {
+        constexpr int TI = Shape<SH>::TI, TJ = Shape<SH>::TJ;
         int r, jrel;
         decode(t, r, jrel);
         const int I = row0 + r;
-        const int J64 = 2 * row0 + jrel;
+        const int J = 2 * row0 + jrel;
         TileDesc d;
-        d.Ai = P + (int64_t)I * NB;
+        d.Ai = P + (int64_t)I * TI;
         d.lda = ldp;
-        d.Bj = P + (int64_t)J64 * BJ;
+        d.Bj = P + (int64_t)J * TJ;
         d.ldb = ldp;
         d.kbeg = kbeg;
         d.KT = (kend - kbeg) / BK;
-        d.C = W + (int64_t)I * NB + (int64_t)J64 * BJ * ld;
+        d.C = W + (int64_t)I * TI + (int64_t)J * TJ * ld;
         d.ldc = ld;
-        d.rowA = I * NB; d.rowB = J64 * BJ; d.colA0 = d.colB0 = 0;   // both operands: the group buffer's map
+        d.rowA = I * TI; d.rowB = J * TJ; d.colA0 = d.colB0 = 0;   // both operands: the group buffer's map
         return d;
     }
 };
@@ -163,9 +181,11 @@ __device__ __forceinline__ double flip_sign(double x) {  // integer pipe, keeps 
 }
 
 // MODE 0: C = acc, 1: C -= acc.  Operands staged by 2-D tensor-map TMA: one elected thread, two instructions per stage.
-template <int MODE, class Src>
+template <int MODE, int SH, class Src>
 __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride, double* sm,
                                                 const CUtensorMap* mapA, const CUtensorMap* mapB) {
+    using TS = Shape<SH>;
+    constexpr int SA = TS::SA, SB = TS::SB, STAGE_DOUBLES = TS::STAGE, NI = TS::NI, NJ = TS::NJ;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g4 = lane >> 2, tq = lane & 3;
@@ -191,7 +211,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
     int p_tile = first_tile, p_kt = 0, produced = 0;
     bool p_valid = p_tile < ntiles;
     TileDesc pd;
-    if (p_valid) pd = src.tile(p_tile);
+    if (p_valid) pd = src.template tile<SH>(p_tile);
     auto produce = [&]() {
         const int s = produced % STAGES;
         if (tid == 0) {
@@ -208,14 +228,14 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             p_kt = 0;
             p_tile += tile_stride;
             p_valid = p_tile < ntiles;
-            if (p_valid) pd = src.tile(p_tile);
+            if (p_valid) pd = src.template tile<SH>(p_tile);
         }
     };
 #pragma unroll 1
     for (int s = 0; s < STAGES - LAG && p_valid; ++s) produce();
 
-    const int64_t coff0 = (wi * 32 + tq * 2);
-    const int joff0 = wj * 32 + g4;
+    const int64_t coff0 = (wi * 8 * NI + tq * 2);
+    const int joff0 = wj * 8 * NJ + g4;
     // pull a tile's C lines (128 rows x 64 columns, read-modify-written by this CTA) towards L2 ahead of use
     auto prefetch_c = [&](const TileDesc& t) {
         int mode = 1;
@@ -223,38 +243,38 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
         if (mode == 1) {
             const double* c0 = t.C + coff0 + (int64_t)joff0 * t.ldc;
 #pragma unroll
-            for (int mj = 0; mj < 4; ++mj)
+            for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni += 2) prefetch_l2(c0 + ni * 8 + (int64_t)(mj * 8) * t.ldc);
+                for (int ni = 0; ni < NI; ni += 2) prefetch_l2(c0 + ni * 8 + (int64_t)(mj * 8) * t.ldc);
         } else if (mode == 2) {
-            if (lane < 8) tma_prefetch_l2(t.C + (int64_t)(warp * 8 + lane) * t.ldc, BI * 8);
+            if (lane < TS::TJ / 8) tma_prefetch_l2(t.C + (int64_t)(warp * (TS::TJ / 8) + lane) * t.ldc, TS::TI * 8);
         }
     };
-    if (MODE == 1 && first_tile < ntiles) prefetch_c(src.tile(first_tile));
+    if (MODE == 1 && first_tile < ntiles) prefetch_c(src.template tile<SH>(first_tile));
 
     int g = 0;  // consumed items
 #pragma unroll 1
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
-        const TileDesc td = src.tile(tile);
+        const TileDesc td = src.template tile<SH>(tile);
         double* cbase = td.C + coff0 + (int64_t)joff0 * td.ldc;
-        double acc[4][4][2];
+        double acc[NJ][NI][2];
         if (MODE == 1) {
             // C is read straight into the accumulators at tile start (its lines were prefetched into L2 one tile
             // ago); the DMMAs then run on -C so that the epilogue is a sign flip and a store, with no load latency.
 #pragma unroll
-            for (int mj = 0; mj < 4; ++mj)
+            for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
+                for (int ni = 0; ni < NI; ++ni) {
                     const double2 v = *reinterpret_cast<const double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc);
                     acc[mj][ni][0] = v.x;
                     acc[mj][ni][1] = v.y;
                 }
-            if (tile + tile_stride < ntiles) prefetch_c(src.tile(tile + tile_stride));  // while this tile computes
+            if (tile + tile_stride < ntiles) prefetch_c(src.template tile<SH>(tile + tile_stride));  // while this tile computes
         } else {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NJ; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+                for (int b = 0; b < NI; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         }
 
 #pragma unroll 1
@@ -264,9 +284,9 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             mbar_wait(&full[s], (g / STAGES) & 1);
             if (MODE == 1 && kt == 0) {
 #pragma unroll
-                for (int mj = 0; mj < 4; ++mj)
+                for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) {
+                    for (int ni = 0; ni < NI; ++ni) {
                         acc[mj][ni][0] = flip_sign(acc[mj][ni][0]);
                         acc[mj][ni][1] = flip_sign(acc[mj][ni][1]);
                     }
@@ -275,15 +295,15 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             const double* sB = sA + BK * SA;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
-                double a[4], b[4];
+                double a[NJ], b[NI];
 #pragma unroll
-                for (int mj = 0; mj < 4; ++mj) a[mj] = sB[(kk * 4 + tq) * SB + wj * 32 + mj * 8 + g4];
+                for (int mj = 0; mj < NJ; ++mj) a[mj] = sB[(kk * 4 + tq) * SB + wj * 8 * NJ + mj * 8 + g4];
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) b[ni] = sA[(kk * 4 + tq) * SA + wi * 32 + ni * 8 + g4];
+                for (int ni = 0; ni < NI; ++ni) b[ni] = sA[(kk * 4 + tq) * SA + wi * 8 * NI + ni * 8 + g4];
 #pragma unroll
-                for (int mj = 0; mj < 4; ++mj)
+                for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
+                    for (int ni = 0; ni < NI; ++ni) dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
             }
             // Release the stage only after this warp's fragment loads have RETURNED: ptxas is free to hoist the
             // arrive above the trailing DMMAs (it has no register dependence on them), and an mbarrier arrive
@@ -294,9 +314,9 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
         }
 
 #pragma unroll
-        for (int mj = 0; mj < 4; ++mj)
+        for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
+            for (int ni = 0; ni < NI; ++ni) {
                 double2 v;
                 if (MODE == 1) {
                     v.x = flip_sign(acc[mj][ni][0]);
@@ -315,13 +335,13 @@ trsm3_kernel(TrsmSrc src, int ntiles, const __grid_constant__ CUtensorMap mapW, 
     extern __shared__ __align__(128) double sm[];
     pdl_trigger();   // small grid: let the trailing update become resident behind it
     pdl_wait();
-    gemm_persistent<0>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
+    gemm_persistent<0, 1>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
 }
 
 // residual block: r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block (deterministic two-half sum)
 __device__ __forceinline__ void syrk_residual_block(const SyrkSrc& src, const double* __restrict__ yk,
                                                     double* __restrict__ rvec, int res_col0, double* sm) {
-    const int I = src.row0 + (int)blockIdx.x;
+    const int I = src.res_row0 + (int)blockIdx.x;
     const int tid = threadIdx.x;
     const int row = tid & (NB - 1), half = tid >> 7;
     const double* p = src.P + (int64_t)I * NB + row + (int64_t)(res_col0 + half * 64) * src.ldp;
@@ -336,14 +356,15 @@ __device__ __forceinline__ void syrk_residual_block(const SyrkSrc& src, const do
 // Blocks [0, nres) update the residual r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block
 // (deterministic two-half sum); they come FIRST so they are not left waiting for a slot behind the persistent
 // tile workers, blocks [nres, nres + nctas).
+template <int SH>
 __global__ void __launch_bounds__(256, 2)
 syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
              int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb) {
     extern __shared__ __align__(128) double sm[];
     pdl_wait();
     if ((int)blockIdx.x >= nres) {
-        // same buffer, two boxes: 132 rows for the 128-row operand, 68 rows for the 64-row one
-        gemm_persistent<1>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
+        // same buffer, two boxes: TI + 4 rows for the i operand, TJ + 4 rows for the j operand
+        gemm_persistent<1, SH>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
     } else {
         syrk_residual_block(src, yk, rvec, res_col0, sm);
     }

@@ -127,6 +127,8 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     }
     printf("trsm7 R=%d (%d tiles): %.2f us per launch (%s)\n", Rb, 4 * Rb, ms * 1000 / 50, cudaGetErrorString(cudaGetLastError()));
+    { long long tt[8]; cudaMemcpyFromSymbol(tt, g_t7_trace, sizeof(tt));
+      printf("   CTA 0: operands landed +%lld, solve +%lld, tile stored +%lld cycles\n", tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2]); }
     cudaFree(Wb); cudaFree(Pb);
   }
   return 0;
