@@ -108,6 +108,8 @@ int main() {
     if (b < 3) { printf(" | update done"); for (int w : {1, 2, 3, 5, 6, 7, 9, 10, 11}) printf(" %6lld", tw[b][1][w] - t[1]); }
     printf("\n");
   }
+  { static long long fs[4][4]; cudaMemcpyFromSymbol(fs, g_p7_fsync, sizeof(fs));
+    for (int b = 0; b < 3; ++b) printf("  block %d follower 0 (since load): follow done %lld, fenced %lld, barrier passed %lld, critical units done %lld, all critical done %lld\n", b, tw[b][0][1] - t[1], fs[b][0] - t[1], fs[b][1] - t[1], fs[b][2] - t[1], fs[b][3] - t[1]); }
   static long long tf[4][8][4], tcn[4][8];
   cudaMemcpyFromSymbol(tf, g_p7_fol, sizeof(tf)); cudaMemcpyFromSymbol(tcn, g_p7_chn, sizeof(tcn));
   for (int b = 0; b < 2; ++b) {
