@@ -80,7 +80,8 @@ int g_farm_potrf_version = 3;
 int g_small_tiles = 1;   // PSOAP_SMALL_TILES=0: keep 128 x 64 tiles for the critical block-column updates too
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
-int g_pdl = 64;        // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
+int g_pdl = 256;       // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
+                       // (64 -> 256 with the 32-row panel-solve tiles and 64 x 32 update tiles: N = 2000 0.78 -> 0.72 ms)
 int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 int set_kernel_attributes() {
