@@ -53,10 +53,11 @@ inline int64_t padded_dim(int64_t n) { return (n + NB - 1) / NB * NB; }
 PFN_cuTensorMapEncodeTiled g_encode_tiled = nullptr;
 
 // column-major FP64 matrix [rows, cols] with leading dimension ld; box = {box_rows, 16 columns}
-int make_tensor_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tensor_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols = BK) {
     const cuuint64_t gdim[2] = {rows, cols};
     const cuuint64_t gstride[1] = {ld * 8};
-    const cuuint32_t box[2] = {box_rows, (cuuint32_t)BK};
+    const cuuint32_t box[2] = {box_rows, box_cols};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -223,10 +224,16 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
                   const int* sentinel, double* result) {
     const int64_t ldp = ws.Nt;
     CUtensorMap mapW, mapLinv, mapPa[2], mapPb[2], mapPas[2], mapPbs[2];   // ..s: boxes of the small tile shape
+    CUtensorMap mapWblk, mapWt, mapL7[3];                                   // chain 7: diagonal block, panel tile, L_kk below its sub-blocks
     {
         const uint64_t Nt = (uint64_t)T_total * NB;
         int rcm = make_tensor_map(&mapW, W, Nt, Nt, (uint64_t)ld, SA);
         if (!rcm) rcm = make_tensor_map(&mapLinv, ws.Linv, NB, NB, NB, SB);
+        if (!rcm) rcm = make_tensor_map(&mapWblk, W, Nt, Nt, (uint64_t)ld, P7_LD, NB);
+        if (!rcm) rcm = make_tensor_map(&mapWt, W, Nt, Nt, (uint64_t)ld, T7_RS, NB);
+        if (!rcm) rcm = make_tensor_map(&mapL7[0], ws.Linv, NB, NB, NB, T7_LS0, 32);
+        if (!rcm) rcm = make_tensor_map(&mapL7[1], ws.Linv, NB, NB, NB, T7_LS1, 32);
+        if (!rcm) rcm = make_tensor_map(&mapL7[2], ws.Linv, NB, NB, NB, T7_LS2, 32);
         for (int q = 0; q < 2 && !rcm; ++q) {
             rcm = make_tensor_map(&mapPa[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SA);
             if (!rcm) rcm = make_tensor_map(&mapPb[q], ws.P[q], (uint64_t)ldp, (uint64_t)MAX_GROUP * NB, (uint64_t)ldp, SB);
@@ -245,7 +252,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     auto potrf = [&](cudaStream_t s, int kb) {
         if (chain == 7)   // blocked: one chain warp, DMMA followers and rank-32 updates (chain.cuh, experimental)
             launch_k(potrf_diag7_kernel, 1, P7_THREADS, POTRF7_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv,
-                     ws.Xd, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
+                     ws.Xd, ws.rvec, ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result, mapWblk);
         else
             launch_k(potrf_diag3_kernel, 1, 256, POTRF_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv, ws.rvec,
                      ws.y + (int64_t)kb * NB, ws.acc, ws.info, sentinel, (int)(kb == T_elim - 1), result);
@@ -256,7 +263,8 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
             Trsm7Args a;
             a.W = W; a.ld = ld; a.kb = kb; a.Lfac = ws.Linv; a.Xd = ws.Xd;
             a.P = pbuf(q) + (int64_t)col0 * ldp; a.ldp = ldp; a.ntiles = 4 * R;
-            launch_k(trsm7_kernel, std::min(4 * R, g_num_sms), T7_THREADS, TRSM7_SMEM, s, ln.pdl, a);
+            launch_k(trsm7_kernel, std::min(4 * R, g_num_sms), T7_THREADS, TRSM7_SMEM, s, ln.pdl, a, mapWt, mapL7[0], mapL7[1],
+                     mapL7[2]);
             return;
         }
         TrsmSrc src;

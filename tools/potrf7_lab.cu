@@ -5,9 +5,19 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cudaTypedefs.h>
 #include <vector>
 #include "../psoap_b200/csrc/chain.cuh"
 using namespace psoap;
+
+static PFN_cuTensorMapEncodeTiled g_enc = nullptr;
+static CUtensorMap tmap(const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  if (!g_enc) { void* fn = nullptr; cudaDriverEntryPointQueryResult q; cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q); g_enc = (PFN_cuTensorMapEncodeTiled)fn; }
+  CUtensorMap m; const cuuint64_t gd[2] = {rows, cols}; const cuuint64_t gs[1] = {ld * 8}; const cuuint32_t bx[2] = {box_rows, box_cols}; const cuuint32_t es[2] = {1, 1};
+  CUresult r = g_enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled failed %d\n", (int)r);
+  return m;
+}
 
 static void host_chol(const std::vector<double>& A, int lda, int n, std::vector<long double>& L) {
   L.assign(n * n, 0.0L);
@@ -32,6 +42,8 @@ int main() {
   cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF7_SMEM);
   cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM7_SMEM);
   printf("POTRF7_SMEM = %d bytes, TRSM7_SMEM = %d bytes\n", POTRF7_SMEM, TRSM7_SMEM);
+  const CUtensorMap mWblk = tmap(W, Nt, Nt, Nt, P7_LD, n), mWt = tmap(W, Nt, Nt, Nt, T7_RS, n);
+  const CUtensorMap mL0 = tmap(Lfac, n, n, n, T7_LS0, 32), mL1 = tmap(Lfac, n, n, n, T7_LS1, 32), mL2 = tmap(Lfac, n, n, n, T7_LS2, 32);
   for (int tc = 0; tc < 4; ++tc) {
     std::vector<double> h((size_t)Nt * Nt, NAN), hr(Nt, 0.0);   // NaN wherever the kernels must not read
     for (int i = 0; i < Nt; ++i) {
@@ -63,9 +75,9 @@ int main() {
     cudaMemcpy(W, h.data(), (size_t)Nt * Nt * 8, cudaMemcpyHostToDevice); cudaMemcpy(r, hr.data(), Nt * 8, cudaMemcpyHostToDevice);
     cudaMemset(acc, 0, 64); cudaMemset(info, 0, 8); cudaMemset(Lfac, 0xff, n * n * 8); cudaMemset(y, 0xff, Nt * 8); cudaMemset(P, 0xff, (size_t)Nt * n * 8);
     cudaMemset(Xd, 0xff, 4 * XD_BLOCK * 8);
-    potrf_diag7_kernel<<<1, P7_THREADS, POTRF7_SMEM>>>(W, Nt, 0, tc == 2 ? 40 : 0, Lfac, Xd, r, y, acc, info, nullptr, 1, res);
+    potrf_diag7_kernel<<<1, P7_THREADS, POTRF7_SMEM>>>(W, Nt, 0, tc == 2 ? 40 : 0, Lfac, Xd, r, y, acc, info, nullptr, 1, res, mWblk);
     Trsm7Args a; a.W = W; a.ld = Nt; a.kb = 0; a.Lfac = Lfac; a.Xd = Xd; a.P = P; a.ldp = Nt; a.ntiles = 4 * R;
-    trsm7_kernel<<<tc == 1 ? 5 : 4 * R, T7_THREADS, TRSM7_SMEM>>>(a);   // case 1: fewer CTAs than tiles (persistent loop)
+    trsm7_kernel<<<tc == 1 ? 5 : 4 * R, T7_THREADS, TRSM7_SMEM>>>(a, mWt, mL0, mL1, mL2);   // case 1: fewer CTAs than tiles (persistent loop)
     cudaError_t e = cudaDeviceSynchronize();
     std::vector<double> gL(n * n), gy(n), gP((size_t)Nt * n), gX(4 * XD_BLOCK); double gacc[8], gres[4]; int ginfo[2];
     cudaMemcpy(gL.data(), Lfac, n * n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(gy.data(), y, n * 8, cudaMemcpyDeviceToHost);
@@ -91,7 +103,7 @@ int main() {
       cudaEventRecord(e0);
       for (int w = 0; w < 50; ++w) {
         if (ver == 3) potrf_diag3_kernel<<<1, 256, POTRF_SMEM>>>(W, Nt, 0, 0, Linv, r, y, acc, info, nullptr, 1, res);
-        else potrf_diag7_kernel<<<1, P7_THREADS, POTRF7_SMEM>>>(W, Nt, 0, 0, Lfac, Xd, r, y, acc, info, nullptr, 1, res);
+        else potrf_diag7_kernel<<<1, P7_THREADS, POTRF7_SMEM>>>(W, Nt, 0, 0, Lfac, Xd, r, y, acc, info, nullptr, 1, res, mWblk);
       }
       cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     }
@@ -125,7 +137,8 @@ int main() {
     Trsm7Args a; a.W = Wb; a.ld = Ntb; a.kb = 0; a.Lfac = Lfac; a.Xd = Xd; a.P = Pb; a.ldp = Ntb; a.ntiles = 4 * Rb;
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
-      for (int w = 0; w < 50; ++w) trsm7_kernel<<<4 * Rb < 148 ? 4 * Rb : 148, T7_THREADS, TRSM7_SMEM>>>(a);
+      const CUtensorMap mWtb = tmap(Wb, Ntb, n, Ntb, T7_RS, n);
+      for (int w = 0; w < 50; ++w) trsm7_kernel<<<4 * Rb < 148 ? 4 * Rb : 148, T7_THREADS, TRSM7_SMEM>>>(a, mWtb, mL0, mL1, mL2);
       cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     }
     printf("trsm7 R=%d (%d tiles): %.2f us per launch (%s)\n", Rb, 4 * Rb, ms * 1000 / 50, cudaGetErrorString(cudaGetLastError()));
