@@ -157,9 +157,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
-    ap.add_argument("--nbranch", type=int, default=32)
+    ap.add_argument("--nbranch", type=int, default=0, help="chunks in flight per GPU (0: 32, or 64 for chunks of N <= 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.nbranch <= 0:   # small chunks: more of them in flight (C6: 31.0 evals/s with 32 branches, 34.0 with 64)
+        args.nbranch = 64 if args.workload == "C6" else 32
     if args.impl == "reference":
         return run_reference(args)
 

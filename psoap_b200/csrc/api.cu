@@ -248,7 +248,9 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     const int G = g_group ? g_group : (ln.group ? ln.group : (T_total >= 96 ? 4 : 2));
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
-    const int chain = ln.chain ? ln.chain : g_potrf_version;
+    // a very large matrix has hundreds of 32-row panel-solve tiles per panel: the GEMM panel solve wins again
+    // (N = 32768: 342 vs 350 ms)
+    const int chain = ln.chain ? ln.chain : (T_total >= 192 ? 3 : g_potrf_version);
     auto potrf = [&](cudaStream_t s, int kb) {
         if (chain == 7)   // blocked: one chain warp, DMMA followers and rank-32 updates (chain.cuh, experimental)
             launch_k(potrf_diag7_kernel, 1, P7_THREADS, POTRF7_SMEM, s, ln.pdl, (const double*)W, ld, kb, pad, ws.Linv,
@@ -791,6 +793,7 @@ struct psoap_farm {
     std::vector<int> item_prio;       // CUDA launch priority of each item's kernels (larger chunk = more urgent)
     bool lookahead = false;
     bool direct = false;              // issue the kernels on every call instead of replaying the captured graph
+    int chain_hint = 0;               // psoap_chunk.reserved of the first chunk: 3 | 7 forces the chain links
     int launches = 0;
 };
 
@@ -823,7 +826,10 @@ int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
             ln.group = f->lookahead ? 0 : 4;
             ln.pdl = pdl;
-            ln.chain = f->lookahead ? 0 : g_farm_potrf_version;   // fewer than 8 branches: chain latency is exposed
+            // chain links: the caller's choice (psoap_chunk.reserved = 3 | 7, the same on every rank of a partitioned
+            // farm so that the bits do not depend on the number of GPUs), else by exposure of the chain latency
+            ln.chain = (f->chain_hint == 3 || f->chain_hint == 7) ? f->chain_hint
+                                                                  : (f->lookahead ? 0 : g_farm_potrf_version);
             g_launch_prio = f->item_prio[it];
             rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, f->mu, gp, ws, f->flags + it, f->results + 4 * it);
             g_launch_prio = 0;
@@ -893,6 +899,7 @@ int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const ps
     f->model = model; f->ncomp = model_ncomp(model); f->norb = model_norb(model);
     f->nchunks = nchunks; f->nprop = nprop; f->nitems = nitems; f->nbranch = nbranch; f->mu = mu_GP;
     f->chunks.assign(chunks, chunks + nchunks);
+    f->chain_hint = chunks[0].reserved;
     char* p = (char*)workspace;
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
     f->p_buf = (double*)take((size_t)nprop * P_STRIDE * 8);

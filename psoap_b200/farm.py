@@ -103,6 +103,9 @@ class ChunkFarm:
             for k2, v in host.items():
                 hb[off[k2]:off[k2] + v.nbytes] = v.view(np.uint8).reshape(-1)
             d = descs[k]
+            # chain links chosen from the GLOBAL problem, not from this rank's share: fewer than 8 (proposal, chunk) pairs
+            # in all -> the latency chain (7), else the throughput chain (3); same bits on 1, 2, 4 or 8 GPUs
+            d.reserved = 7 if self.n_chunks * self.n_proposals < 8 else 3
             d.N, d.n_epochs = len(host["fl"]), len(host["dates"])
             d.lwl, d.epoch, d.fl = base + off["lwl"], base + off["epoch"], base + off["fl"]
             d.sigma, d.dates = base + off["sigma"], base + off["dates"]

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2: full GPU suite, bench lines for every workload, launch lists, ncu captures of the dominant kernels
+set -x
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r2_tests_final.log 2>&1
+tail -4 gpurun_out/r2_tests_final.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c4.json 2> gpurun_out/r2_bench_c4.err; tail -c 300 gpurun_out/r2_bench_c4.err
+for w in C1 C2 C3 C5 C6; do python bench.py --workload $w --steps 10 --warmup 3 > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; head -c 200 gpurun_out/r2_bench_$w.json; echo; done
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref.json 2> gpurun_out/r2_bench_ref.err
+python tools/time_lnlike.py --big > gpurun_out/r2_time_lnlike_final.txt 2>&1; cat gpurun_out/r2_time_lnlike_final.txt
+python tools/time_predict.py > gpurun_out/r2_time_predict_final.txt 2>&1; cat gpurun_out/r2_time_predict_final.txt
+python tools/fill_once.py 300 20 > gpurun_out/r2_fill_time_final.txt 2>&1; cat gpurun_out/r2_fill_time_final.txt
