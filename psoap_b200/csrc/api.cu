@@ -181,25 +181,17 @@ struct Lanes {
 // while its predecessor in the stream still runs, and waits in pdl_wait() (common.cuh).  Only SMALL grids are
 // pre-staged: a waiting CTA holds its SM slot, which is free when the chain is the only work (small matrices, the
 // tail of a large one) and costly while a big trailing update wants every slot.
-// g_launch_prio: CUDA priority (0 = default, negative = more urgent) given to the kernels launched next by this host
-// thread; the farm sets it per chunk (largest chunks first), which also reaches the kernel nodes of a captured graph.
-thread_local int g_launch_prio = 0;
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, int pdl_max,
                      Args&&... args) {
     const bool pdl = (int)(grid.x * grid.y * grid.z) <= pdl_max;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     int n = 0;
     if (pdl) {
         at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
-    if (g_launch_prio != 0) {
-        at[n].id = cudaLaunchAttributePriority;
-        at[n].val.priority = g_launch_prio;
         ++n;
     }
     cfg.attrs = at; cfg.numAttrs = n;
@@ -790,7 +782,6 @@ struct psoap_farm {
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> side_events;
     std::vector<double*> item_vel;    // device velocity table of each item
-    std::vector<int> item_prio;       // CUDA launch priority of each item's kernels (larger chunk = more urgent)
     bool lookahead = false;
     bool direct = false;              // issue the kernels on every call instead of replaying the captured graph
     int chain_hint = 0;               // psoap_chunk.reserved of the first chunk: 3 | 7 forces the chain links
@@ -830,9 +821,7 @@ int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
             // farm so that the bits do not depend on the number of GPUs), else by exposure of the chain latency
             ln.chain = (f->chain_hint == 3 || f->chain_hint == 7) ? f->chain_hint
                                                                   : (f->lookahead ? 0 : g_farm_potrf_version);
-            g_launch_prio = f->item_prio[it];
             rc = launch_chunk(ln, f->ncomp, ch.N, zs, ch.fl, ch.sigma, f->mu, gp, ws, f->flags + it, f->results + 4 * it);
-            g_launch_prio = 0;
             if (rc) break;
         }
         cudaEventRecord(f->events[b], sb);
@@ -940,26 +929,24 @@ int psoap_farm_create_batched(psoap_farm** out, int model, int nchunks, const ps
         load[b] += n * n * n;
     }
 
-    // Launch priorities: the device has a few priority levels (0 = default .. `hi`, more negative = more urgent); the
-    // items are ranked by size and the levels dealt out evenly, largest chunks most urgent, so that the chunks with
-    // the longest chains of dependent panels get SM slots whenever they have work and the small ones fill the gaps
-    // and the drain at the end of an evaluation.
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        const char* pe = getenv("PSOAP_FARM_PRIO");
-        const bool use = pe ? (atoi(pe) != 0) : true;
-        const int nlev = lo - hi + 1;          // hi <= lo
-        f->item_prio.assign(nitems, 0);
-        if (use && nlev > 1 && nitems > 1)
-            for (int r = 0; r < nitems; ++r)   // order[] is sorted by decreasing N
-                f->item_prio[order[r]] = hi + (int)((int64_t)r * nlev / nitems);
-    }
-
     // capture the whole evaluation into one CUDA graph
     f->streams.resize(nbranch + 1);
     f->events.resize(nbranch + 1);
-    for (auto& s : f->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    {
+        // Branch b carries the b-th largest items first (LPT order): its stream gets the matching priority level, which a
+        // captured kernel node inherits (PSOAP_FARM_PRIO=0: all equal).  Measured neutral on a B200 (one rank's share of
+        // an 8-GPU run: 28.50 ms either way; a launch-attribute variant likewise): the drain at the end of an evaluation
+        // is not a matter of which chunk gets the free SM slots first.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* pe = getenv("PSOAP_FARM_PRIO");
+        const int mode = pe ? (atoi(pe) != 0) : 1;
+        const int nlev = lo - hi + 1;
+        for (int b = 0; b <= nbranch; ++b) {
+            const int pr = (mode == 1 && b < nbranch && nlev > 1) ? hi + (int)((int64_t)b * nlev / nbranch) : lo;
+            cudaStreamCreateWithPriority(&f->streams[b], cudaStreamNonBlocking, pr);
+        }
+    }
     for (auto& ev : f->events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     f->side_streams.resize(nbranch);
     f->side_events.resize(2 * nbranch);
