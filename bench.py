@@ -301,6 +301,11 @@ def main():
         k_syrk = 512 if args.workload in ("C4", "C5", "C6") else 256   # the rank the orchestration uses for this workload
         _lib.check(lib.psoap_bench_syrk(m_syrk, k_syrk, 20, ctypes.byref(avg_ms), ctypes.byref(fl)))
         achieved = fl.value / (avg_ms.value * 1e-3) * 1e-12
+        # the same launch with its partial last round dealt out as quarter tiles: faster ALONE, slower in every path that
+        # ships (api.cu g_tail_split), so it is reported beside the shipped configuration, not instead of it
+        t_ms = ctypes.c_double()
+        _lib.check(lib.psoap_bench_syrk_split(m_syrk, k_syrk, 20, 1, ctypes.byref(t_ms), ctypes.byref(fl)))
+        achieved_tail = fl.value / (t_ms.value * 1e-3) * 1e-12
         step_tflops = flops_total * value * 1e-12 / world
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "syrk_traffic.json")
@@ -342,7 +347,13 @@ def main():
                            "duration does not exist there); step_tflops_per_gpu = algorithmic flops of the timed "
                            "region (sum over chunks of N^3/3 + 2N^2) / its measured time",
                     "step_tflops_per_gpu": step_tflops, "step_frac": step_tflops / peak.value,
-                    "algorithmic_flops_per_eval": flops_total, "fill": fill}
+                    "algorithmic_flops_per_eval": flops_total, "fill": fill,
+                    "alone_with_quarter_tail": {
+                        "achieved": achieved_tail, "frac": achieved_tail / peak.value,
+                        "note": "same launch, the partial last round of its tiles dealt out as quarter tiles "
+                                "(psoap_bench_syrk_split): what wave quantisation costs this kernel when NOTHING else "
+                                "runs.  Not shipped: in the farm that round is filled by the other branches' kernels "
+                                "and the less efficient quarter tiles cost 3 % of the step (PSOAP_TAIL=1)"}}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,

@@ -181,6 +181,9 @@ int psoap_fp64_peak_tflops(double *tflops_out);
  * lower triangle, CUDA events on the launching stream.  flops_per_launch is the algorithmic count K m (m + 1)
  * (DSYRK convention; the upper halves of the diagonal tiles are computed but not counted). Synchronous. */
 int psoap_bench_syrk(int64_t m, int K, int reps, double *avg_ms_out, double *flops_per_launch_out);
+/* The same launch with the partial last round of tiles dealt out as quarter tiles (tail_split = 1) or whole
+ * (0): psoap_bench_syrk uses the library's shipped setting (0, see api.cu g_tail_split for the measurements). */
+int psoap_bench_syrk_split(int64_t m, int K, int reps, int tail_split, double *avg_ms_out, double *flops_per_launch_out);
 /* The likelihood's INTERNAL fill (csrc/fill.cuh fill_lower_kernel) written into a caller-provided matrix, for the
  * entry-wise parity tests against psoap/matrix_functions.pyx:125-144 (+ covariance.py:322, data.py:40-63).
  * W_dev: column-major [Np, ld], Np = N rounded up to 128, ld >= Np and even; data index i lives at i + (Np - N);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "psoap_farm_destroy": (ctypes.c_int, [vp]),
     "psoap_fp64_peak_tflops": (ctypes.c_int, [c_double_p]),
     "psoap_bench_syrk": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
+    "psoap_bench_syrk_split": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
     "psoap_debug_fill_lower": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp,
                                               c_double_p, c_double_p, ctypes.c_double, vp, ctypes.c_int64, vp, vp]),
     "psoap_bench_fill": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, vp, c_double_p, c_double_p,

@@ -78,6 +78,11 @@ int g_yield_lookahead = 1;
 // 32-row tile).  PSOAP_POTRF sets both, PSOAP_FARM_POTRF the farm's.
 int g_potrf_version = 7;
 int g_farm_potrf_version = 3;
+// PSOAP_TAIL=1: the partial last round of a trailing update is dealt out as quarter tiles (syrk_split).  Measured on
+// a B200: the kernel ALONE gains (m = 4096, K = 512: 29.4 -> 31.7 TFLOP/s, m = 8192: 33.0 -> 33.9), every path that
+// ships loses, because there the partial round is already covered by other work: the 256-chunk farm 217.7 -> 224.1 ms
+// (the other branches' kernels), a lone N = 6000 matrix 3.71 -> 3.74 ms (the look-ahead's next panels).  Off.
+int g_tail_split = 0;
 int g_small_tiles = 1;   // PSOAP_SMALL_TILES=0: keep 128 x 64 tiles for the critical block-column updates too
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
@@ -85,6 +90,18 @@ int g_pdl = 256;       // direct issue: grids up to this many CTAs are launched 
                        // (64 -> 256 with the 32-row panel-solve tiles and 64 x 32 update tiles: N = 2000 0.78 -> 0.72 ms)
 int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
+// How a trailing update of `ntiles` 128 x 64 tiles is dealt out: `nmain` tiles to `nctas` CTAs (persistent round-robin,
+// or one tile each when `one_per_cta`), and the partial last round, `ntiles - nmain` tiles, as 4 quarter-tile CTAs each
+// when that is shorter than one more whole-tile round (3 quarter rounds or fewer).
+struct SyrkSplit { int nmain, nctas, nquarters; };
+inline SyrkSplit syrk_split(int ntiles, bool one_per_cta, bool allow_tail) {
+    const int slots = g_ctas_per_sm * g_num_sms;
+    SyrkSplit sp{ntiles, 0, 0};
+    const int rem = ntiles % slots;
+    if (allow_tail && rem > 0 && 4 * rem <= 3 * slots) { sp.nmain = ntiles - rem; sp.nquarters = 4 * rem; }
+    sp.nctas = one_per_cta ? sp.nmain : std::min(sp.nmain, slots);
+    return sp;
+}
 int set_kernel_attributes() {
     std::call_once(g_attr_once, [] {
         cudaError_t e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
@@ -104,6 +121,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_SMALL_TILES")) g_small_tiles = atoi(c);
+        if (const char* c = getenv("PSOAP_TAIL")) g_tail_split = atoi(c);
         if (const char* c = getenv("PSOAP_FARM_POTRF")) g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
         if (e == cudaSuccess) {
@@ -282,14 +300,16 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         // Under look-ahead the bulk update (part 2) gives up persistence: one tile per CTA, so SM slots free up
         // continuously and the high-priority side stream (next group's potrf/trsm) is scheduled into them.
         const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
-        const int nctas = ntiles > 0 ? (yield_slots ? ntiles : persistent_ctas(ntiles)) : 0;
         const double* yk = ws.y + (int64_t)std::max(ykb, 0) * NB;
-        if (sh == 2)
+        if (sh == 2) {
+            const int nctas = persistent_ctas(ntiles);
             launch_k(syrk3_kernel<2>, nctas + nres, 256, Shape<2>::SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec,
-                     res_col0, mapPas[q & 1], mapPbs[q & 1]);
-        else
-            launch_k(syrk3_kernel<1>, nctas + nres, 256, GEMM_SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec, res_col0,
-                     mapPa[q & 1], mapPb[q & 1]);
+                     res_col0, mapPas[q & 1], mapPbs[q & 1], mapPas[q & 1], mapPbs[q & 1]);
+        } else {
+            const SyrkSplit sp = syrk_split(ntiles, yield_slots, part != 1 && g_tail_split != 0);
+            launch_k(syrk3_kernel<1>, nres + sp.nctas + sp.nquarters, 256, GEMM_SMEM, s, ln.pdl, src, sp.nmain, sp.nctas, nres,
+                     yk, ws.rvec, res_col0, mapPa[q & 1], mapPb[q & 1], mapPas[q & 1], mapPbs[q & 1]);
+        }
         ++g_launches;
     };
     const int ngroups = (T_elim + G - 1) / G;
@@ -1032,6 +1052,12 @@ int psoap_farm_destroy(psoap_farm* f) {
 // Times the trailing-update kernel (syrk3_kernel, the dominant kernel of the path) alone: `reps` launches of the rank-K update (K a multiple of 128) of an m x m lower triangle (m a multiple of 128), CUDA events on a private
 // stream.  flops_per_launch is the algorithmic count K * m * (m + 1) (DSYRK convention).
 int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flops_per_launch_out) {
+    return psoap_bench_syrk_split(m, K, reps, g_tail_split, avg_ms_out, flops_per_launch_out);
+}
+
+// The same with the quarter-tile tail (syrk_split) forced on or off: the configuration that ships is
+// psoap_bench_syrk's; this entry exists so that the bench line can show what the tail costs the kernel when it runs alone.
+int psoap_bench_syrk_split(int64_t m, int K, int reps, int tail_split, double* avg_ms_out, double* flops_per_launch_out) {
     if (m < NB || m % NB || reps < 1 || !avg_ms_out || K < NB || K % NB || K > 2048)
         return fail(PSOAP_ERR_ARG, "psoap_bench_syrk: bad arguments");
     int rc = set_kernel_attributes();
@@ -1056,13 +1082,16 @@ int psoap_bench_syrk(int64_t m, int K, int reps, double* avg_ms_out, double* flo
     SyrkSrc src;
     src.W = W; src.ld = m; src.row0 = 0; src.res_row0 = 0; src.kbeg = 0; src.kend = K; src.P = P; src.ldp = m; src.part = 0; src.ncol1 = 2;
     src.pf_mode = g_pf_mode;
-    const int nctas = persistent_ctas(ntiles);
-    CUtensorMap mapPa, mapPb;
+    const SyrkSplit sp = syrk_split(ntiles, false, tail_split != 0);
+    CUtensorMap mapPa, mapPb, mapQa, mapQb;
     rc = make_tensor_map(&mapPa, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SA);
     if (!rc) rc = make_tensor_map(&mapPb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, SB);
+    if (!rc) rc = make_tensor_map(&mapQa, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, Shape<2>::SA);
+    if (!rc) rc = make_tensor_map(&mapQb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, Shape<2>::SB);
     if (rc) return rc;
     auto launch = [&]() {
-        syrk3_kernel<1><<<nctas + R, 256, GEMM_SMEM, st>>>(src, ntiles, nctas, R, y, r, 0, mapPa, mapPb);
+        syrk3_kernel<1><<<R + sp.nctas + sp.nquarters, 256, GEMM_SMEM, st>>>(src, sp.nmain, sp.nctas, R, y, r, 0, mapPa, mapPb,
+                                                                              mapQa, mapQb);
         ++g_launches;
     };
     for (int w = 0; w < 2; ++w) launch();

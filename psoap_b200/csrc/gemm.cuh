@@ -168,6 +168,24 @@ struct SyrkSrc {
     }
 };
 
+// The last, partial round of a persistent launch as QUARTER tiles (64 x 32, the SH = 2 shape): quarter t of the tail
+// belongs to the 128 x 64 tile first + t / 4.  Each quarter is one CTA behind the persistent ones in the same grid, so
+// the hardware hands them to SM slots as these free up (see syrk3_kernel).  Same k order per entry: same bits.
+struct SyrkTailSrc {
+    SyrkSrc base;
+    int first;
+    int pf_mode;
+    template <int SH = 2>
+    __device__ __forceinline__ TileDesc tile(int t) const {
+        TileDesc d = base.template tile<1>(first + (t >> 2));
+        const int qi = t & 1, qj = (t >> 1) & 1;
+        d.Ai += qi * Shape<2>::TI; d.rowA += qi * Shape<2>::TI;
+        d.Bj += qj * Shape<2>::TJ; d.rowB += qj * Shape<2>::TJ;
+        d.C += qi * Shape<2>::TI + (int64_t)qj * Shape<2>::TJ * d.ldc;
+        return d;
+    }
+};
+
 // number of tiles of a syrk launch over R row tiles
 __host__ __device__ inline int syrk_ntiles(int R, int part, int ncol1) {
     const int h = ncol1 >> 1;
@@ -258,7 +276,13 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
         const TileDesc td = src.template tile<SH>(tile);
         double* cbase = td.C + coff0 + (int64_t)joff0 * td.ldc;
         double acc[NJ][NI][2];
-        if (MODE == 1) {
+        // trailing update: a warp whose sub-tile lies strictly above the diagonal (6 of the 16 warps of a diagonal
+        // tile pair) has nothing to do: the factorisation reads the lower triangle only.  It keeps the pipeline's
+        // barrier protocol and leaves the tensor pipe to the other warps of the SM.
+        const bool idle = (MODE == 1) && (td.rowA + wi * 8 * NI + 8 * NI - 1 < td.rowB + wj * 8 * NJ);
+        if (MODE == 1 && idle) {
+            if (tile + tile_stride < ntiles) prefetch_c(src.template tile<SH>(tile + tile_stride));
+        } else if (MODE == 1) {
             // C is read straight into the accumulators at tile start (its lines were prefetched into L2 one tile
             // ago); the DMMAs then run on -C so that the epilogue is a sign flip and a store, with no load latency.
 #pragma unroll
@@ -282,7 +306,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             if (p_valid) produce();  // refills the stage consumed LAG items ago
             const int s = g % STAGES;
             mbar_wait(&full[s], (g / STAGES) & 1);
-            if (MODE == 1 && kt == 0) {
+            if (MODE == 1 && kt == 0 && !idle) {
 #pragma unroll
                 for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
@@ -293,6 +317,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             }
             const double* sA = sm + s * STAGE_DOUBLES;
             const double* sB = sA + BK * SA;
+            if (!idle) {
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
                 double a[NJ], b[NI];
@@ -305,6 +330,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 #pragma unroll
                     for (int ni = 0; ni < NI; ++ni) dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
             }
+            }
             // Release the stage only after this warp's fragment loads have RETURNED: ptxas is free to hoist the
             // arrive above the trailing DMMAs (it has no register dependence on them), and an mbarrier arrive
             // is not ordered behind ld.shared still queued in the LSU.  fence.acq_rel.cta (MEMBAR.CTA) drains them.
@@ -313,6 +339,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
+        if (!idle) {
 #pragma unroll
         for (int mj = 0; mj < NJ; ++mj)
 #pragma unroll
@@ -326,6 +353,7 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
                 }
                 *reinterpret_cast<double2*>(cbase + ni * 8 + (int64_t)(mj * 8) * td.ldc) = v;
             }
+        }
     }
 }
 
@@ -355,18 +383,28 @@ __device__ __forceinline__ void syrk_residual_block(const SyrkSrc& src, const do
 
 // Blocks [0, nres) update the residual r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block
 // (deterministic two-half sum); they come FIRST so they are not left waiting for a slot behind the persistent
-// tile workers, blocks [nres, nres + nctas).
+// tile workers, blocks [nres, nres + nctas), which walk tiles [0, ntiles) round-robin.  Blocks behind those (SH = 1
+// only) each take ONE quarter of the tiles from `ntiles` on: the partial last round of a persistent launch, cut into
+// 64 x 32 pieces that the block scheduler deals out as the persistent CTAs retire (m = 4096, K = 512: 1056 tiles on
+// 296 slots are 3 rounds + 168 tiles; as a 4th round those keep 57 % of the slots busy for a whole tile time).
 template <int SH>
 __global__ void __launch_bounds__(256, 2)
 syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restrict__ yk, double* __restrict__ rvec,
-             int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb) {
+             int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb,
+             const __grid_constant__ CUtensorMap mapQa, const __grid_constant__ CUtensorMap mapQb) {
     extern __shared__ __align__(128) double sm[];
     pdl_wait();
-    if ((int)blockIdx.x >= nres) {
-        // same buffer, two boxes: TI + 4 rows for the i operand, TJ + 4 rows for the j operand
-        gemm_persistent<1, SH>(src, ntiles, (int)blockIdx.x - nres, nctas, sm, &mapPa, &mapPb);
-    } else {
+    const int b = (int)blockIdx.x - nres;
+    if (b < 0) {
         syrk_residual_block(src, yk, rvec, res_col0, sm);
+    } else if (b < nctas) {
+        // same buffer, two boxes: TI + 4 rows for the i operand, TJ + 4 rows for the j operand
+        gemm_persistent<1, SH>(src, ntiles, b, nctas, sm, &mapPa, &mapPb);
+    } else if constexpr (SH == 1) {
+        SyrkTailSrc tail;
+        tail.base = src; tail.first = ntiles; tail.pf_mode = 0;
+        const int q = b - nctas;
+        gemm_persistent<1, 2>(tail, q + 1, q, 1 << 30, sm, &mapQa, &mapQb);
     }
 }
 

@@ -684,9 +684,9 @@ def test_farm_many_proposals(oracle, torch_cuda):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"PSOAP_POTRF": "3"}, {"PSOAP_POTRF": "7", "PSOAP_GROUP": "4"},
                                  {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"},
-                                 {"PSOAP_FARM_PRIO": "0"}],
+                                 {"PSOAP_FARM_PRIO": "0"}, {"PSOAP_TAIL": "1"}],
                          ids=["inverse-chain-everywhere", "blocked-chain-everywhere-group4", "no-pdl-no-lookahead", "pdl-everywhere",
-                              "farm-without-priorities"])
+                              "farm-without-priorities", "quarter-tile-tail"])
 def test_alternative_kernel_paths(env, torch_cuda):
     """The library's environment switches select alternative kernels / launch modes for the same contract (the blocked
     diagonal factorisation + blocked panel solve of csrc/chain.cuh, launch attributes).  They are read once at load
@@ -695,7 +695,7 @@ def test_alternative_kernel_paths(env, torch_cuda):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child_env = dict(os.environ, **env)
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
-           "-k", "lnlike_golden or tile_boundaries or predict_golden or farm_vs_oracle"]
+           "-k", "lnlike_golden or tile_boundaries or predict_golden or farm_vs_oracle or package_default_hyperparameters_large"]
     out = subprocess.run(cmd, cwd=root, env=child_env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout

@@ -1,4 +1,4 @@
-"""Run the dominant kernel alone (for ncu captures): python tools/bench_syrk.py [m] [reps]"""
+"""Run the dominant kernel alone (for ncu captures): python tools/bench_syrk.py [m] [reps] [K] [tail_split]"""
 import ctypes
 import os
 import sys
@@ -11,5 +11,6 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 lib = _lib.load()
 ms, fl = ctypes.c_double(), ctypes.c_double()
-_lib.check(lib.psoap_bench_syrk(m, K, reps, ctypes.byref(ms), ctypes.byref(fl)))
-print("m=%d K=%d avg_ms=%.4f tflops=%.2f" % (m, K, ms.value, fl.value / ms.value * 1e-9))
+tail = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+_lib.check(lib.psoap_bench_syrk_split(m, K, reps, tail, ctypes.byref(ms), ctypes.byref(fl)))
+print("m=%d K=%d tail_split=%d avg_ms=%.4f tflops=%.2f" % (m, K, tail, ms.value, fl.value / ms.value * 1e-9))
