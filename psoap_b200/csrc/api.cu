@@ -108,7 +108,7 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM7_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK1_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<2>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -307,7 +307,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
                      res_col0, mapPas[q & 1], mapPbs[q & 1], mapPas[q & 1], mapPbs[q & 1]);
         } else {
             const SyrkSplit sp = syrk_split(ntiles, yield_slots, part != 1 && g_tail_split != 0);
-            launch_k(syrk3_kernel<1>, nres + sp.nctas + sp.nquarters, 256, GEMM_SMEM, s, ln.pdl, src, sp.nmain, sp.nctas, nres,
+            launch_k(syrk3_kernel<1>, nres + sp.nctas + sp.nquarters, 256, SYRK1_SMEM, s, ln.pdl, src, sp.nmain, sp.nctas, nres,
                      yk, ws.rvec, res_col0, mapPa[q & 1], mapPb[q & 1], mapPas[q & 1], mapPbs[q & 1]);
         }
         ++g_launches;
@@ -594,7 +594,8 @@ int psoap_lnlike_host(int ncomp, int64_t N, const double* lwl_f, const double* l
         result->logdet = result->quad = result->info = 0.0;
         return PSOAP_OK;
     }
-    if (!lwl_f || !fl || !sigma) return fail(PSOAP_ERR_ARG, "psoap_lnlike_host: null vector");
+    if (!lwl_f || !fl || !sigma || (ncomp > 1 && !lwl_g) || (ncomp > 2 && !lwl_h))
+        return fail(PSOAP_ERR_ARG, "psoap_lnlike_host: null vector");
     std::lock_guard<std::mutex> lock(g_hc.mu);
     const size_t vec = align_up((size_t)N * 8, 256);
     const size_t need = psoap_lnlike_workspace_bytes(N) + 5 * vec + 256;
@@ -1090,7 +1091,7 @@ int psoap_bench_syrk_split(int64_t m, int K, int reps, int tail_split, double* a
     if (!rc) rc = make_tensor_map(&mapQb, P, (uint64_t)m, (uint64_t)K, (uint64_t)m, Shape<2>::SB);
     if (rc) return rc;
     auto launch = [&]() {
-        syrk3_kernel<1><<<R + sp.nctas + sp.nquarters, 256, GEMM_SMEM, st>>>(src, sp.nmain, sp.nctas, R, y, r, 0, mapPa, mapPb,
+        syrk3_kernel<1><<<R + sp.nctas + sp.nquarters, 256, SYRK1_SMEM, st>>>(src, sp.nmain, sp.nctas, R, y, r, 0, mapPa, mapPb,
                                                                               mapQa, mapQb);
         ++g_launches;
     };

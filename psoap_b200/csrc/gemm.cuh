@@ -29,7 +29,7 @@
 
 namespace psoap {
 
-constexpr int BI = 128, BJ = 64, BK = 16, STAGES = 4;
+constexpr int BI = 128, BJ = 64, BK = 16;
 constexpr int GEMM_WARPS = 8;
 // Tile shapes.  SH = 1: 128 x 64 output tile (warp tile 32 x 32), the throughput shape of the trailing update.
 // SH = 2: 64 x 32 (warp tile 16 x 16), four times as many tiles of a quarter of the work each: the LATENCY shape, for
@@ -40,12 +40,17 @@ struct Shape {
     static constexpr int TI = BI / SH, TJ = BJ / SH;          // tile rows (i), tile columns (j)
     static constexpr int SA = TI + 4, SB = TJ + 4;            // padded operand rows in shared memory (= TMA box rows)
     static constexpr int STAGE = BK * SA + BK * SB;           // doubles per pipeline stage
-    static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
+    // Pipeline depth.  A 64 x 32 tile is short of work per stage (4 DMMAs per warp and k-step), so what bounds it is
+    // how many TMA round trips (~1 us each) it has in flight: 8 stages (6 in flight) against 4 (2 in flight).
+    static constexpr int NSTAGE = SH == 1 ? 4 : 8;
+    static constexpr int SMEM = NSTAGE * STAGE * 8 + 2 * NSTAGE * 8;
     static constexpr int NI = TI / 32, NJ = TJ / 16;          // 8 x 8 atoms per warp along i and j (warps 4 x 2)
 };
 constexpr int SA = Shape<1>::SA, SB = Shape<1>::SB;
 constexpr int STAGE_DOUBLES = Shape<1>::STAGE;
 constexpr int GEMM_SMEM = Shape<1>::SMEM;
+// syrk3_kernel<1> may carry quarter-tile CTAs (the SH = 2 pipeline) behind its persistent ones: room for either
+constexpr int SYRK1_SMEM = Shape<1>::SMEM > Shape<2>::SMEM ? Shape<1>::SMEM : Shape<2>::SMEM;
 
 // 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG): box {rows, 16 k-columns} of a column-major matrix lands as
 // [16][rows] in shared memory; with a box of 132 (68) rows that IS the padded, bank-conflict-free stage layout, so a
@@ -203,7 +208,7 @@ template <int MODE, int SH, class Src>
 __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int first_tile, int tile_stride, double* sm,
                                                 const CUtensorMap* mapA, const CUtensorMap* mapB) {
     using TS = Shape<SH>;
-    constexpr int SA = TS::SA, SB = TS::SB, STAGE_DOUBLES = TS::STAGE, NI = TS::NI, NJ = TS::NJ;
+    constexpr int SA = TS::SA, SB = TS::SB, STAGE_DOUBLES = TS::STAGE, NI = TS::NI, NJ = TS::NJ, STAGES = TS::NSTAGE;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g4 = lane >> 2, tq = lane & 3;
