@@ -1195,6 +1195,26 @@ int psoap_debug_syrk_tiles(int R, int part, int ncol1, int* rows_out, int* cols_
     return n;
 }
 
+#ifdef PSOAP_TIMELINE
+// Lab builds only (tools/timeline.py): copies the CTA time stamps out (7 int64 per record) and resets the counter.
+extern "C" int psoap_debug_timeline(long long* out, int cap) {
+    unsigned n = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(n)));
+    n = std::min(n, TL_CAP);
+    std::vector<TlRec> h(n);
+    if (n) CUDA_TRY(cudaMemcpyFromSymbol(h.data(), g_tl, (size_t)n * sizeof(TlRec)));
+    const int m = std::min<int>((int)n, cap);
+    for (int i = 0; i < m; ++i) {
+        out[7 * i] = (long long)h[i].t_in; out[7 * i + 1] = (long long)h[i].t_go; out[7 * i + 2] = (long long)h[i].t_out;
+        out[7 * i + 3] = h[i].kernel; out[7 * i + 4] = h[i].block; out[7 * i + 5] = h[i].nblocks; out[7 * i + 6] = h[i].smid;
+    }
+    const unsigned zero = 0;
+    CUDA_TRY(cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(zero)));
+    return (int)n;
+}
+#endif
+
 int psoap_fp64_peak_tflops(double* tflops_out) {
     if (!tflops_out) return fail(PSOAP_ERR_ARG, "psoap_fp64_peak_tflops: null");
     int dev = 0, sms = 0;

@@ -185,8 +185,10 @@ potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     const int tid = threadIdx.x;
     const int ti = tid & 15, tc = tid >> 4;
     const double* A = W + (int64_t)kb * NB + (int64_t)kb * NB * ld;
+    TL_IN();
     pdl_trigger();   // one CTA: the panel solve may become resident on the other SMs while this block is factored
     pdl_wait();
+    TL_GO(5);
 
     double M[8][8];
 #pragma unroll
@@ -209,6 +211,7 @@ potrf_diag3_kernel(const double* __restrict__ W, int64_t ld, int kb, int pad, do
     potrf3_block_steps<7>(M, ti, tc, tid, Xs, colb, rowb, scal, dval);
     __syncthreads();
     potrf_epilogue(tid, kb, pad, Xs, dval, rs, red, Linv, yk, acc, info, sentinel, is_last, result);
+    TL_OUT();
 }
 
 // Register-resident DMMA loop: the FP64 tensor-pipe peak used as the roofline denominator.

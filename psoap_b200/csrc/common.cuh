@@ -156,4 +156,27 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Lab builds only (-DPSOAP_TIMELINE, tools/timeline.py): every CTA leaves (entry, start after the programmatic-launch
+// wait, end) stamps of the GPU's global timer, so that the overlap of the streams of one factorisation can be drawn.
+#ifdef PSOAP_TIMELINE
+struct TlRec { unsigned long long t_in, t_go, t_out; int kernel, block, nblocks, smid; };
+constexpr unsigned TL_CAP = 1u << 18;
+__device__ TlRec g_tl[TL_CAP];
+__device__ unsigned int g_tl_n;
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_IN() unsigned tl_i = 0xffffffffu; unsigned long long tl_tin = 0; if (threadIdx.x == 0) tl_tin = psoap::tl_now()
+#define TL_GO(kid) do { if (threadIdx.x == 0) { tl_i = atomicAdd(&psoap::g_tl_n, 1u); if (tl_i < psoap::TL_CAP) { \
+    unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); psoap::TlRec& r_ = psoap::g_tl[tl_i]; r_.t_in = tl_tin; \
+    r_.t_go = psoap::tl_now(); r_.t_out = 0; r_.kernel = (kid); r_.block = blockIdx.x; r_.nblocks = gridDim.x; r_.smid = (int)sm_; } } } while (0)
+#define TL_OUT() do { if (threadIdx.x == 0 && tl_i < psoap::TL_CAP) psoap::g_tl[tl_i].t_out = psoap::tl_now(); } while (0)
+#else
+#define TL_IN() do { } while (0)
+#define TL_GO(kid) do { } while (0)
+#define TL_OUT() do { } while (0)
+#endif
+
 }  // namespace psoap

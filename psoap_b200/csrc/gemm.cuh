@@ -366,9 +366,12 @@ __device__ __forceinline__ void gemm_persistent(const Src& src, int ntiles, int 
 __global__ void __launch_bounds__(256, 2)
 trsm3_kernel(TrsmSrc src, int ntiles, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapLinv) {
     extern __shared__ __align__(128) double sm[];
+    TL_IN();
     pdl_trigger();   // small grid: let the trailing update become resident behind it
     pdl_wait();
+    TL_GO(6);
     gemm_persistent<0, 1>(src, ntiles, blockIdx.x, gridDim.x, sm, &mapW, &mapLinv);
+    TL_OUT();
 }
 
 // residual block: r_I -= P_I[:, res_col0 .. res_col0+128) y for row tile I = row0 + block (deterministic two-half sum)
@@ -398,7 +401,9 @@ syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restr
              int res_col0, const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb,
              const __grid_constant__ CUtensorMap mapQa, const __grid_constant__ CUtensorMap mapQb) {
     extern __shared__ __align__(128) double sm[];
+    TL_IN();
     pdl_wait();
+    TL_GO(SH == 1 ? (src.part == 1 ? 8 : 3) : 4);
     const int b = (int)blockIdx.x - nres;
     if (b < 0) {
         syrk_residual_block(src, yk, rvec, res_col0, sm);
@@ -411,6 +416,7 @@ syrk3_kernel(SyrkSrc src, int ntiles, int nctas, int nres, const double* __restr
         const int q = b - nctas;
         gemm_persistent<1, 2>(tail, q + 1, q, 1 << 30, sm, &mapQa, &mapQb);
     }
+    TL_OUT();
 }
 
 

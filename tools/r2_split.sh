@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-for sp in 0 1; do echo "SPLIT=$sp"; PSOAP_SPLIT=$sp timeout 300 python tools/time_lnlike.py; done
+for sp in 0 1 2 3; do echo "SPLIT=$sp"; PSOAP_SPLIT=$sp timeout 300 python tools/time_lnlike.py | head -4; done
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "lnlike_golden or tile_boundaries or predict or farm_vs_oracle or vs_reference_cpu or package_default or lnlike_vs_oracle or calibration or repeatable" 2>&1 | tail -5
-for sp in 0 1; do echo "SPLIT=$sp C1"; PSOAP_SPLIT=$sp timeout 300 python bench.py --workload C1 --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | head -c 200; echo; done
 } > gpurun_out/r2_split.txt 2>&1
 cat gpurun_out/r2_split.txt
