@@ -92,11 +92,13 @@ def workload_config(workload, n_chunks, model, world, nbranch):
                           if world > 1 else "none (single rank)"}
 
 
-def cpu_farm(workload, steps, warmup):
+def cpu_farm(workload, steps, warmup, blas_threads=None):
     """oracle/cpu_farm.py as a subprocess (never shares this process's CUDA context): the reference's CPU path on
     all host cores, one BLAS thread per worker, chunks handed out dynamically, largest first."""
     cmd = [sys.executable, "-m", "oracle.cpu_farm", "--config", workload, "--sample", str(CPU_SAMPLE.get(workload, 1)),
            "--steps", str(steps), "--warmup", str(warmup)]
+    if blas_threads:
+        cmd += ["--blas-threads", str(blas_threads)]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle.cpu_farm failed: " + out.stderr[-400:])
@@ -157,11 +159,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
-    ap.add_argument("--nbranch", type=int, default=0, help="chunks in flight per GPU (0: 32, or 64 for chunks of N <= 2048)")
+    ap.add_argument("--nbranch", type=int, default=0, help="chunks in flight per GPU (0: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.nbranch <= 0:   # small chunks: more of them in flight (C6: 31.0 evals/s with 32 branches, 34.0 with 64)
-        args.nbranch = 64 if args.workload == "C6" else 32
+    if args.nbranch <= 0:   # measured: C4 4.60 evals/s with 32 branches, 4.62 with 64 (4.66 with rank-1024 updates); C6 31.0 / 34.0
+        args.nbranch = 64
     if args.impl == "reference":
         return run_reference(args)
 
@@ -171,11 +173,18 @@ def main():
 
     # CPU baseline first (rank 0, N=1 only), as its own process, before this process touches CUDA
     cpu_baseline, cpu_run = None, None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline and args.workload != "C5":
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
-            # bounded sample (C4: 64 of the 256 chunks), 1 warm-up pass + 2 timed passes
-            cpu_run = cpu_farm(args.workload, 2, 1)
+            # bounded sample (C4: 64 of the 256 chunks), 1 warm-up pass + 2 timed passes (C5, one N = 32768 matrix:
+            # a single pass of about a minute)
+            cpu_run = cpu_farm(args.workload, *((1, 0) if args.workload == "C5" else (2, 1)))
             cpu_baseline = cpu_baseline_record(cpu_run)
+            if cpu_run["n_chunks"] == 1 and args.workload != "C5":
+                # BASELINE.md asks for the pair "BLAS threads = all cores" and "= 1" on the single-matrix configurations
+                one = cpu_farm(args.workload, 1, 0, blas_threads=1)
+                cpu_baseline["blas_threads_1"] = {"value": one["evals_per_s"], "unit": "evals/s",
+                                                  "fill_fraction": one["fill_fraction"],
+                                                  "lapack_fraction": one["lapack_fraction"]}
         except Exception as exc:  # report, do not hide
             cpu_baseline = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
                             "sample": "failed: " + str(exc)[-300:]}

@@ -62,7 +62,7 @@ def sample_indices(n_total, sample):
     return sorted(set(int((k + 0.5) * n_total / sample) for k in range(sample)))
 
 
-def run(config="C4", sample=64, steps=1, warmup=0, workers=None, full=False):
+def run(config="C4", sample=64, steps=1, warmup=0, workers=None, full=False, blas_threads=None):
     from oracle import oracle as orc
     from psoap_b200 import synthetic
     model, chunks = synthetic.config_chunks(config)
@@ -74,7 +74,7 @@ def run(config="C4", sample=64, steps=1, warmup=0, workers=None, full=False):
     p = synthetic.default_params(model)
     cores = os.cpu_count() or 1
     workers = max(1, min(workers or cores, len(sub)))
-    blas_threads = max(1, cores // workers)
+    blas_threads = blas_threads or max(1, cores // workers)
     use_ref = orc.ref_matrix_functions() is not None
     order = sorted(range(len(sub)), key=lambda k: -Ns[k])       # largest first
     ctx = mp.get_context("fork")
@@ -119,5 +119,6 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--workers", type=int, default=None)
     ap.add_argument("--full", action="store_true", help="evaluate every chunk of the configuration (no scaling)")
+    ap.add_argument("--blas-threads", type=int, default=None, help="BLAS threads per worker (default: cores // workers)")
     a = ap.parse_args()
-    print(json.dumps(run(a.config, a.sample, a.steps, a.warmup, a.workers, a.full)))
+    print(json.dumps(run(a.config, a.sample, a.steps, a.warmup, a.workers, a.full, a.blas_threads)))

@@ -88,7 +88,8 @@ int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
 int g_pdl = 256;       // direct issue: grids up to this many CTAs are launched with programmatic stream serialization
                        // (64 -> 256 with the 32-row panel-solve tiles and 64 x 32 update tiles: N = 2000 0.78 -> 0.72 ms)
-int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4 forces it
+int g_group = 0;  // 0: automatic (see launch_factor); PSOAP_GROUP=2|4|8 forces it
+int g_farm_group = 8;   // PSOAP_FARM_GROUP: panels per trailing update inside the graph farm
 inline int persistent_ctas(int ntiles) { return std::max(1, std::min(ntiles, g_ctas_per_sm * g_num_sms)); }
 // How a trailing update of `ntiles` 128 x 64 tiles is dealt out: `nmain` tiles to `nctas` CTAs (persistent round-robin,
 // or one tile each when `one_per_cta`), and the partial last round, `ntiles - nmain` tiles, as 4 quarter-tile CTAs each
@@ -122,6 +123,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_SMALL_TILES")) g_small_tiles = atoi(c);
         if (const char* c = getenv("PSOAP_TAIL")) g_tail_split = atoi(c);
+        if (const char* c = getenv("PSOAP_FARM_GROUP")) g_farm_group = (atoi(c) >= 8) ? 8 : (atoi(c) >= 4) ? 4 : 2;
         if (const char* c = getenv("PSOAP_FARM_POTRF")) g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
         if (e == cudaSuccess) {
@@ -135,7 +137,7 @@ int set_kernel_attributes() {
         }
         if (const char* c = getenv("PSOAP_LOOKAHEAD")) g_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_PDL")) g_pdl = atoi(c);
-        if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
+        if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 8) ? 8 : (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -144,7 +146,7 @@ int set_kernel_attributes() {
 
 // Device scratch of one factorisation: W [Nt x Nt] (Nt = padded total dimension), two panel buffers,
 // L_kk^-1, residual, y, accumulators, info.
-constexpr int MAX_GROUP = 4;  // panels per trailing update (rank 128 * G)
+constexpr int MAX_GROUP = 8;  // panels per trailing update (rank 128 * G)
 struct FactorWs {
     double* W;
     double* P[2];   // two group buffers, each column-major [Nt, 128 * MAX_GROUP] (the adjacent panels of a group)
@@ -252,9 +254,10 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         }
         if (rcm) return rcm;
     }
-    // Rank-512 updates (G = 4) are worth their longer panel chain when that chain is hidden anyway (the farm:
-    // measured 4.30 -> 4.37 evals/s on C4) or when the matrix is large (N = 16384: 50.0 -> 49.1 ms); a single
-    // mid-size matrix is faster with G = 2 (N = 9000: 11.2 vs 11.7 ms).
+    // Wide updates are worth their longer panel chain when that chain is hidden anyway: the graph farm runs rank-1024
+    // updates (G = 8: C4 4.30 / 4.37 / 4.40 evals/s at G = 2 / 4 / 8 in their rounds' kernels, 4.62 -> 4.66 now), a
+    // large matrix rank-512 (N = 16384: 50.0 -> 49.1 ms); a single mid-size matrix is faster with G = 2 (N = 9000: 11.2 vs
+    // 11.7 ms).
     const int G = g_group ? g_group : (ln.group ? ln.group : (T_total >= 96 ? 4 : 2));
     auto pbuf = [&](int q) { return ws.P[q & 1]; };
     auto kbeg_of = [&](int q) { return q == 0 ? (pad / BK) * BK : 0; };
@@ -836,7 +839,7 @@ int farm_issue(psoap_farm* f, cudaStream_t s0, int pdl) {
             ln.main = sb;
             ln.side = f->lookahead ? f->side_streams[b] : nullptr;
             ln.e1 = f->side_events[2 * b]; ln.e2 = f->side_events[2 * b + 1];
-            ln.group = f->lookahead ? 0 : 4;
+            ln.group = f->lookahead ? 0 : g_farm_group;
             ln.pdl = pdl;
             // chain links: the caller's choice (psoap_chunk.reserved = 3 | 7, the same on every rank of a partitioned
             // farm so that the bits do not depend on the number of GPUs), else by exposure of the chain latency

@@ -45,7 +45,10 @@ __device__ const double EXP2_64_TAB[64] = {
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
 // Every kernel that evaluates covariance terms keeps a copy of the table in shared memory (lanes index it with
-// different j): call before the kernel's first __syncthreads().
+// different j): call before the kernel's first __syncthreads().  ncu counts 41 % of the fill's shared-memory
+// wavefronts as bank conflicts of these lookups; sixteen interleaved copies (one per lane of a half-warp, conflict
+// free) were measured and are NOT faster (fill_lower at N = 6000: 64.8 us against 62.6): the lookup is not what bounds
+// the kernel, the FP64 pipe is (66 % active).
 __device__ __forceinline__ void load_exp_table(double* tab_sm) {
     if (threadIdx.x < 64) tab_sm[threadIdx.x] = EXP2_64_TAB[threadIdx.x];
 }
@@ -160,7 +163,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // wait, end) stamps of the GPU's global timer, so that the overlap of the streams of one factorisation can be drawn.
 #ifdef PSOAP_TIMELINE
 struct TlRec { unsigned long long t_in, t_go, t_out; int kernel, block, nblocks, smid; };
-constexpr unsigned TL_CAP = 1u << 18;
+constexpr unsigned TL_CAP = 1u << 20;
 __device__ TlRec g_tl[TL_CAP];
 __device__ unsigned int g_tl_n;
 __device__ __forceinline__ unsigned long long tl_now() {

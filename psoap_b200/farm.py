@@ -11,6 +11,7 @@ per-chunk log-likelihoods are combined with a single all-reduce of a length-n_ch
 filled, others zero: exact and order independent), then summed in chunk order like the reference's np.sum.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -105,7 +106,7 @@ class ChunkFarm:
             d = descs[k]
             # chain links chosen from the GLOBAL problem, not from this rank's share: fewer than 8 (proposal, chunk) pairs
             # in all -> the latency chain (7), else the throughput chain (3); same bits on 1, 2, 4 or 8 GPUs
-            d.reserved = 7 if self.n_chunks * self.n_proposals < 8 else 3
+            d.reserved = int(os.environ.get("PSOAP_FARM_CHAIN", 7 if self.n_chunks * self.n_proposals < 8 else 3))
             d.N, d.n_epochs = len(host["fl"]), len(host["dates"])
             d.lwl, d.epoch, d.fl = base + off["lwl"], base + off["epoch"], base + off["fl"]
             d.sigma, d.dates = base + off["sigma"], base + off["dates"]

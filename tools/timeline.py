@@ -45,7 +45,7 @@ def main():
     lib.psoap_debug_timeline.restype = ctypes.c_int
     lib.psoap_debug_timeline.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     model, ne, npx = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    cap = 1 << 18
+    cap = 1 << 20
     buf = (ctypes.c_longlong * (7 * cap))()
     r = time_lnlike.time_chunk(model, ne, npx, reps=3)        # warm
     lib.psoap_debug_timeline(buf, cap)                         # reset
