@@ -255,7 +255,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         if (rcm) return rcm;
     }
     // Wide updates are worth their longer panel chain when that chain is hidden anyway: the graph farm runs rank-1024
-    // updates (G = 8: C4 4.30 / 4.37 / 4.40 evals/s at G = 2 / 4 / 8 in their rounds' kernels, 4.62 -> 4.66 now), a
+    // updates (G = 8: C4 4.62 -> 4.66 evals/s against G = 4 with 64 branches; G = 4 against 2 was 4.30 -> 4.37 in round 1), a
     // large matrix rank-512 (N = 16384: 50.0 -> 49.1 ms); a single mid-size matrix is faster with G = 2 (N = 9000: 11.2 vs
     // 11.7 ms).
     const int G = g_group ? g_group : (ln.group ? ln.group : (T_total >= 96 ? 4 : 2));
