@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2: full GPU suite, bench lines for every workload, launch lists, ncu captures of the dominant kernels
+# round 2, final: full GPU suite, smoke, bench lines for every workload, reference arm, single-call timings
 set -x
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r2_tests_final.log 2>&1

@@ -1,7 +1,7 @@
 """Where the SM slots of a farm evaluation go, from GPU global-timer stamps of every CTA (lab build of the library with
 -DPSOAP_TIMELINE, see tools/timeline.py).
 
-  python tools/timeline_farm.py [nchunks=32] [nbranch=32]
+  python tools/timeline_farm.py [nchunks=32] [nbranch=32] [config=C4]
 
 Prints, per kernel, the CTA count, the summed CTA residence time and its share of the evaluation's slot-time
 (wall x 148 SMs x 2 CTA slots: the trailing update runs 2 CTAs per SM), and per SM the fraction of the wall time with
@@ -31,7 +31,7 @@ def main():
     lib = _lib.load()
     lib.psoap_debug_timeline.restype = ctypes.c_int
     lib.psoap_debug_timeline.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
-    model, chunks = synthetic.config_chunks("C4")
+    model, chunks = synthetic.config_chunks(sys.argv[3] if len(sys.argv) > 3 else "C4")
     chunks = chunks[::max(1, len(chunks) // nchunks)]
     p = synthetic.default_params(model)
     farm = ChunkFarm(model, chunks, nbranch=nbranch)
