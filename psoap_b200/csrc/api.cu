@@ -68,9 +68,10 @@ int make_tensor_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t 
 
 std::once_flag g_attr_once;
 int g_attr_status = 0;
+int g_attr_device = 0;
 int g_num_sms = 148;
 int g_ctas_per_sm = 2;
-int g_yield_lookahead = 1;
+int g_yield_lookahead = -1;  // PSOAP_YIELD_LOOKAHEAD: how the bulk update shares the SMs with the links under look-ahead (see the syrk launch); -1 = by size
 // Chain links (diagonal block + panel solve): 7 = potrf_diag7 + trsm7 (chain.cuh: blocked factorisation with one chain
 // warp, blocked substitution), 3 = potrf_diag3 + trsm3 (explicit 128 x 128 inverse, GEMM panel solve).  7 is the faster
 // chain for a matrix factored on its own (N = 2000: 0.88 vs 1.22 ms, N = 4000: 2.11 vs 2.74 ms); inside the graph farm,
@@ -111,12 +112,18 @@ int set_kernel_attributes() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK1_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape<2>::SMEM);
+        // every kernel of the chain asks for the same (maximal) shared-memory carve-out: CTAs of kernels with different
+        // carve-outs do not share an SM, and the links are meant to run beside the trailing update's CTAs
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag7_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm7_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(trsm3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk3_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int dev = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        g_attr_device = dev;
         g_attr_status = (int)e;
         if (const char* c = getenv("PSOAP_CTAS_PER_SM")) g_ctas_per_sm = std::max(1, std::min(2, atoi(c)));
         if (const char* c = getenv("PSOAP_YIELD_LOOKAHEAD")) g_yield_lookahead = atoi(c);
@@ -141,6 +148,14 @@ int set_kernel_attributes() {
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
+    // Kernel attributes, the SM count, the side lane of the direct API and the host-entry staging buffer belong to the
+    // device that was current at the first call: one process per GPU (how the path is deployed).  A second device in
+    // the same process is refused here rather than failing later with invalid-resource-handle launches.
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != g_attr_device)
+        return fail(PSOAP_ERR_ARG, "psoap_b200 is bound to CUDA device " + std::to_string(g_attr_device) +
+                                       " for the lifetime of the process (one process per GPU); the current device is " +
+                                       std::to_string(dev));
     return PSOAP_OK;
 }
 
@@ -300,17 +315,28 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         const int ntiles = syrk_ntiles(sh * R, part, sh * ncol1);
         const int nres = (part == 2 || ykb < 0) ? 0 : R;
         if (ntiles + nres == 0) return;
-        // Under look-ahead the bulk update (part 2) gives up persistence: one tile per CTA, so SM slots free up
-        // continuously and the high-priority side stream (next group's potrf/trsm) is scheduled into them.
-        const bool yield_slots = (part == 2 && ln.side != nullptr && g_yield_lookahead);
+        // Under look-ahead the bulk update (part 2) must leave room for the links of the next group (high-priority side
+        // stream).  Mode 2 (default): it stays persistent but takes ONE slot per SM and leaves one SM empty, so that every
+        // link finds a slot on every SM at once (a panel-solve CTA, 126 KB of shared memory, fits beside an update CTA,
+        // 102 KB, and not beside two) and the one-CTA diagonal block, which needs a whole SM's shared memory, an empty SM
+        // instead of waiting 20-40 us for two update CTAs to retire.  Mode 1: one tile per CTA on all slots, which free
+        // up continuously.  Mode 0: persistent on all slots (the links then wait for the update to end).  N = 4000 / 6000
+        // / 9000: 1.70 / 3.50 / 9.31 ms in mode 2, 1.75 / 3.64 / 9.39 in mode 1; where the bulk dominates mode 1 wins
+        // (N = 16384: 47.4 vs 47.7 ms, N = 32768: 349 vs 364 ms), so by default mode 2 below 96 panels and mode 1 from there.
+        const int yield_mode = g_yield_lookahead >= 0 ? g_yield_lookahead : (T_total >= 96 ? 1 : 2);
+        const bool yield_slots = (part == 2 && ln.side != nullptr && yield_mode);
         const double* yk = ws.y + (int64_t)std::max(ykb, 0) * NB;
         if (sh == 2) {
             const int nctas = persistent_ctas(ntiles);
             launch_k(syrk3_kernel<2>, nctas + nres, 256, Shape<2>::SMEM, s, ln.pdl, src, ntiles, nctas, nres, yk, ws.rvec,
                      res_col0, mapPas[q & 1], mapPbs[q & 1], mapPas[q & 1], mapPbs[q & 1]);
         } else {
-            const SyrkSplit sp = syrk_split(ntiles, yield_slots, part != 1 && g_tail_split != 0);
-            launch_k(syrk3_kernel<1>, nres + sp.nctas + sp.nquarters, 256, SYRK1_SMEM, s, ln.pdl, src, sp.nmain, sp.nctas, nres,
+            SyrkSplit sp = syrk_split(ntiles, yield_slots && yield_mode == 1, part != 1 && g_tail_split != 0);
+            // mode 2: the bulk update under look-ahead stays persistent but takes ONE slot per SM and leaves one SM empty:
+            // the links find a slot on every SM at once and the one-CTA diagonal block (which needs a whole SM's shared
+            // memory) an empty SM, instead of waiting for update CTAs to retire
+            if (yield_slots && yield_mode == 2) sp.nctas = std::min(sp.nmain, g_num_sms - 1);
+            launch_k(syrk3_kernel<1>, nres + sp.nctas + sp.nquarters, 256, sp.nquarters ? SYRK1_SMEM : GEMM_SMEM, s, ln.pdl, src, sp.nmain, sp.nctas, nres,
                      yk, ws.rvec, res_col0, mapPa[q & 1], mapPb[q & 1], mapPas[q & 1], mapPbs[q & 1]);
         }
         ++g_launches;

@@ -684,9 +684,9 @@ def test_farm_many_proposals(oracle, torch_cuda):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"PSOAP_POTRF": "3"}, {"PSOAP_POTRF": "7", "PSOAP_GROUP": "4"},
                                  {"PSOAP_PDL": "0", "PSOAP_LOOKAHEAD": "0"}, {"PSOAP_PDL": "100000"},
-                                 {"PSOAP_FARM_PRIO": "0"}, {"PSOAP_TAIL": "1"}],
+                                 {"PSOAP_FARM_PRIO": "0", "PSOAP_FARM_GROUP": "4"}, {"PSOAP_TAIL": "1"}],
                          ids=["inverse-chain-everywhere", "blocked-chain-everywhere-group4", "no-pdl-no-lookahead", "pdl-everywhere",
-                              "farm-without-priorities", "quarter-tile-tail"])
+                              "farm-without-priorities-rank512", "quarter-tile-tail"])
 def test_alternative_kernel_paths(env, torch_cuda):
     """The library's environment switches select alternative kernels / launch modes for the same contract (the blocked
     diagonal factorisation + blocked panel solve of csrc/chain.cuh, launch attributes).  They are read once at load
@@ -699,3 +699,24 @@ def test_alternative_kernel_paths(env, torch_cuda):
     out = subprocess.run(cmd, cwd=root, env=child_env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+@pytest.mark.gpu
+def test_second_device_in_one_process_is_refused(torch_cuda):
+    """The library binds to the device of its first call (one process per GPU); another current device is an error,
+    not an invalid-resource-handle launch later."""
+    import ctypes
+    from psoap_b200 import _lib
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    lib = _lib.load()
+    ms, fl = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.psoap_bench_syrk(256, 128, 1, ctypes.byref(ms), ctypes.byref(fl)))     # binds to the current device
+    cur = torch.cuda.current_device()
+    try:
+        torch.cuda.set_device((cur + 1) % torch.cuda.device_count())
+        with pytest.raises(_lib.PsoapError, match="one process per GPU"):
+            _lib.check(lib.psoap_bench_syrk(256, 128, 1, ctypes.byref(ms), ctypes.byref(fl)))
+    finally:
+        torch.cuda.set_device(cur)
