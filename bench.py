@@ -307,7 +307,9 @@ def main():
         _lib.check(lib.psoap_fp64_peak_tflops(ctypes.byref(peak)))
         avg_ms, fl = ctypes.c_double(), ctypes.c_double()
         m_syrk = {"C1": 4096, "C4": 4096, "C6": 1536}.get(args.workload, 8192)
-        k_syrk = 512 if args.workload in ("C4", "C5", "C6") else 256   # the rank the orchestration uses for this workload
+        # the rank the orchestration uses for this workload: 1024 in the graph farm (8 panels per update), 512 for one
+        # very large matrix, 256 for one mid-size matrix
+        k_syrk = 1024 if args.workload in ("C4", "C6") else (512 if args.workload == "C5" else 256)
         _lib.check(lib.psoap_bench_syrk(m_syrk, k_syrk, 20, ctypes.byref(avg_ms), ctypes.byref(fl)))
         achieved = fl.value / (avg_ms.value * 1e-3) * 1e-12
         # the same launch with its partial last round dealt out as quarter tiles: faster ALONE, slower in every path that
