@@ -159,11 +159,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
-    ap.add_argument("--nbranch", type=int, default=0, help="chunks in flight per GPU (0: 64)")
+    ap.add_argument("--nbranch", type=int, default=0, help="chunks in flight per GPU (0: 64; 128 for the small chunks of C6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.nbranch <= 0:   # measured: C4 4.60 evals/s with 32 branches, 4.62 with 64 (4.66 with rank-1024 updates); C6 31.0 / 34.0
-        args.nbranch = 64
+    if args.nbranch <= 0:   # measured: C4 4.60 evals/s with 32 branches, 4.62 with 64 (4.66 with rank-1024 updates), 4.60 with 96;
+        args.nbranch = 128 if args.workload == "C6" else 64   # C6 (N = 1600) 31.0 / 34.2 / 34.9 with 32 / 64 / 128
     if args.impl == "reference":
         return run_reference(args)
 
