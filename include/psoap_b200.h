@@ -52,8 +52,9 @@ typedef struct {
 typedef struct {
     int64_t N;            /* number of unmasked pixels                                                   */
     int32_t n_epochs;
-    int32_t reserved;     /* 0, or 3 | 7 on the FIRST chunk: force the chain-link kernels of the whole farm (a farm
-                           * partitioned over ranks passes the same value everywhere: bits independent of the GPU count) */
+    int32_t reserved;     /* 0, or on the FIRST chunk: low byte 3 | 7 forces the chain-link kernels of the whole farm, the next
+                           * byte 2 | 4 | 8 its panels per trailing update (a farm partitioned over ranks passes the same
+                           * value everywhere: bits independent of the GPU count) */
     const double *lwl;    /* [N] ln-wavelength of the masked, epoch-major flattened pixels (data.py:126)  */
     const int32_t *epoch; /* [N] epoch index of every pixel (what the mask broadcast in data.py:61 encodes) */
     const double *fl;     /* [N] flux                                                                    */

@@ -106,7 +106,12 @@ class ChunkFarm:
             d = descs[k]
             # chain links chosen from the GLOBAL problem, not from this rank's share: fewer than 8 (proposal, chunk) pairs
             # in all -> the latency chain (7), else the throughput chain (3); same bits on 1, 2, 4 or 8 GPUs
-            d.reserved = int(os.environ.get("PSOAP_FARM_CHAIN", 7 if self.n_chunks * self.n_proposals < 8 else 3))
+            # ... and the panels per trailing update likewise: rank-1024 updates (8) when there are at least 64 pairs to
+            # hide their long heads behind, else rank-512 (4)
+            n_pairs = self.n_chunks * self.n_proposals
+            chain = int(os.environ.get("PSOAP_FARM_CHAIN", 7 if n_pairs < 8 else 3))
+            group = int(os.environ.get("PSOAP_FARM_GROUP", 8 if n_pairs >= 64 else 4))
+            d.reserved = chain | (group << 8)
             d.N, d.n_epochs = len(host["fl"]), len(host["dates"])
             d.lwl, d.epoch, d.fl = base + off["lwl"], base + off["epoch"], base + off["fl"]
             d.sigma, d.dates = base + off["sigma"], base + off["dates"]
