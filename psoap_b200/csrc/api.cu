@@ -84,6 +84,7 @@ int g_farm_potrf_version = 3;
 // ships loses, because there the partial round is already covered by other work: the 256-chunk farm 217.7 -> 224.1 ms
 // (the other branches' kernels), a lone N = 6000 matrix 3.71 -> 3.74 ms (the look-ahead's next panels).  Off.
 int g_tail_split = 0;
+int g_single_rows = 24;  // PSOAP_SINGLE_ROWS: a lone matrix goes to single-panel groups once this many row blocks remain (0: never)
 int g_small_tiles = 1;   // PSOAP_SMALL_TILES=0: keep 128 x 64 tiles for the critical block-column updates too
 int g_pf_mode = 2;
 int g_lookahead = 1;   // direct API: next group's head on a high-priority side stream
@@ -130,6 +131,7 @@ int set_kernel_attributes() {
         if (const char* c = getenv("PSOAP_POTRF")) g_potrf_version = g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_SMALL_TILES")) g_small_tiles = atoi(c);
         if (const char* c = getenv("PSOAP_TAIL")) g_tail_split = atoi(c);
+        if (const char* c = getenv("PSOAP_SINGLE_ROWS")) g_single_rows = atoi(c);
         if (const char* c = getenv("PSOAP_FARM_GROUP")) g_farm_group = (atoi(c) >= 8) ? 8 : (atoi(c) >= 4) ? 4 : 2;
         if (const char* c = getenv("PSOAP_FARM_POTRF")) g_farm_potrf_version = (atoi(c) == 7) ? 7 : 3;
         if (const char* c = getenv("PSOAP_PF_MODE")) g_pf_mode = atoi(c);
@@ -144,7 +146,7 @@ int set_kernel_attributes() {
         }
         if (const char* c = getenv("PSOAP_LOOKAHEAD")) g_lookahead = atoi(c);
         if (const char* c = getenv("PSOAP_PDL")) g_pdl = atoi(c);
-        if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 8) ? 8 : (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : 0);
+        if (const char* c = getenv("PSOAP_GROUP")) g_group = (atoi(c) >= 8) ? 8 : (atoi(c) >= 4) ? 4 : (atoi(c) >= 2 ? 2 : (atoi(c) == 1 ? 1 : 0));
     });
     if (g_attr_status != 0)
         return fail(PSOAP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)g_attr_status));
@@ -341,12 +343,27 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
         }
         ++g_launches;
     };
-    const int ngroups = (T_elim + G - 1) / G;
-    auto group_size = [&](int q) { return std::min(G, T_elim - q * G); };
+    // Group boundaries.  Uniform groups of G, except at the END of a matrix factored on its own (look-ahead, chain 7):
+    // once fewer than g_single_rows row blocks remain the trailing update is shorter than the links it runs beside,
+    // the chain is all there is, and single panels (no in-group column update, a rank-128 update of ONE block column
+    // before the next diagonal block) make the shortest chain: 38 us per panel against 48.  Measured with 0 / 16 / 24 / 36
+    // such rows: N = 4000 1.706 / 1.675 / 1.647 / 1.625 ms, N = 6000 3.514 / 3.491 / 3.442 / 3.526, N = 9000 9.31 / 9.29 / 9.25 / 9.33.
+    std::vector<int> gstart;
+    {
+        const bool lone = ln.side != nullptr && chain == 7 && g_group == 0;
+        for (int a = 0; a < T_elim;) {
+            const int g = (lone && T_total - a <= g_single_rows) ? 1 : G;
+            gstart.push_back(a);
+            a += std::min(g, T_elim - a);
+        }
+        gstart.push_back(T_elim);
+    }
+    const int ngroups = (int)gstart.size() - 1;
+    auto group_size = [&](int q) { return gstart[q + 1] - gstart[q]; };
     // everything of group q that precedes its big update: for each panel g: (column update with the group's
     // earlier panels, which also carries the residual update of panel g-1), potrf, trsm
     auto head = [&](cudaStream_t s, int q) -> int {
-        const int a = q * G, n = group_size(q);
+        const int a = gstart[q], n = group_size(q);
         for (int g = 0; g < n; ++g) {
             const int kb = a + g;
             if (g > 0) syrk(s, q, kb, g * NB, 1, 2, kb - 1, (g - 1) * NB);   // block column kb, K = 128 g
@@ -357,7 +374,7 @@ int launch_factor(const Lanes& ln, double* W, int64_t ld, int T_elim, int T_tota
     };
     // the big update of group q with all its panels (the residual blocks apply its last panel)
     auto update = [&](cudaStream_t s, int q, int part, int ncol1) {
-        const int a = q * G, n = group_size(q);
+        const int a = gstart[q], n = group_size(q);
         syrk(s, q, a + n, n * NB, part, ncol1, a + n - 1, (n - 1) * NB);
     };
     int rc = head(ln.main, 0);
